@@ -1,0 +1,192 @@
+"""Torch-facing wrappers over the C ABI.  Torch is plumbing only here: device
+memory, the current stream, and a device guard; all arithmetic runs in libantq.so.
+
+Reference functions replaced (A/ = ant_quantization/, O/ = olive_quantization/):
+  lut_nearest   quant_cuda.quant                  A/quant/quant.cpp:26-28
+  fakequant     Quantizer._forward                A/antquant/quant_modules.py:535-551
+                OliVe _forward + OVP              O/antquant/quant_modules.py:295-330
+  absmax        alpha init                        A/antquant/quant_modules.py:473-477
+  mse_sweep     search_mse candidate loop         A/antquant/quant_modules.py:299-306
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def _dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("antq: unsupported dtype %s (float32, float16, bfloat16)" % t.dtype)
+
+
+def _need_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("antq: %s must be a CUDA tensor -- there is no CPU path" % name)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Codebook:
+    """Device-resident prepared codebook + its host-side header."""
+
+    def __init__(self, buf, info, k_normal, k_out):
+        self.buf = buf
+        self.info = info
+        self.k_normal = k_normal
+        self.k_out = k_out
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    @property
+    def n_entries(self):
+        return self.info.n_entries
+
+    def describe(self):
+        return self.info.as_dict()
+
+
+def prepare_codebook(grid, outliers=None):
+    """grid / outliers: 1-D CUDA tensors (any float dtype; values are taken as fp32,
+    like `quant_grid.type_as(x)` narrowed into the kernel's float smem table)."""
+    _need_cuda(grid, "grid")
+    with torch.cuda.device(grid.device):
+        g = grid.detach().reshape(-1).to(torch.float32).contiguous()
+        o = None
+        if outliers is not None and outliers.numel() > 0:
+            o = outliers.detach().reshape(-1).to(device=g.device, dtype=torch.float32).contiguous()
+        k_out = 0 if o is None else o.numel()
+        if g.numel() < 1 or g.numel() + k_out > _lib.MAX_GRID:
+            raise ValueError("antq: grid must have 1..%d entries (got %d + %d)" % (_lib.MAX_GRID, g.numel(), k_out))
+        buf = torch.empty(lib.antq_codebook_bytes(), dtype=torch.uint8, device=g.device)
+        check(lib.antq_codebook_prepare(_ptr(g), g.numel(), _ptr(o), k_out, _ptr(buf), _stream()),
+              "antq_codebook_prepare")
+        info = _lib.CodebookInfo()
+        check(lib.antq_codebook_info_get(_ptr(buf), ctypes.byref(info), _stream()), "antq_codebook_info_get")
+        return Codebook(buf, info, g.numel(), k_out)
+
+
+def lut_nearest(x, cb, want_codes=False):
+    _need_cuda(x, "x")
+    with torch.cuda.device(x.device):
+        xc = x.contiguous()
+        z = torch.empty_like(xc)
+        codes = torch.empty(xc.shape, dtype=torch.int16, device=xc.device) if want_codes else None
+        check(lib.antq_lut_nearest(_ptr(xc), _ptr(z), _ptr(codes), xc.numel(), _dtype_code(xc), _ptr(cb.buf),
+                                   _stream()), "antq_lut_nearest")
+    return (z, codes) if want_codes else z
+
+
+def _rows_cols(x, per_row):
+    if per_row:
+        rows = x.shape[0] if x.dim() > 0 else 1
+        return rows, (x.numel() // rows if rows else 0)
+    return 1, x.numel()
+
+
+def _alpha_arg(alpha, rows, per_row, device):
+    a = alpha.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    if a.numel() != (rows if per_row else 1):
+        raise ValueError("antq: alpha has %d entries, expected %d" % (a.numel(), rows if per_row else 1))
+    return a
+
+
+def fakequant(x, alpha, cb, per_row, ovp=False, want_codes=False, flags=0, out=None):
+    """Fused scale -> nearest -> (OVP) -> STE -> rescale.  x: contiguous CUDA tensor;
+    alpha: fp32 CUDA tensor with x.shape[0] entries (per_row) or one entry."""
+    _need_cuda(x, "x")
+    if not x.is_contiguous():
+        raise RuntimeError("antq: x must be contiguous")
+    with torch.cuda.device(x.device):
+        rows, cols = _rows_cols(x, per_row)
+        a = _alpha_arg(alpha, rows, per_row, x.device)
+        if out is None:
+            out = torch.empty_like(x)
+        codes = torch.empty(x.shape, dtype=torch.int16, device=x.device) if want_codes else None
+        fl = flags | (_lib.FLAG_OVP if ovp else 0)
+        check(lib.antq_fakequant(_ptr(x), _ptr(out), _ptr(codes), _ptr(a), int(bool(per_row)), rows, cols,
+                                 _dtype_code(x), _ptr(cb.buf), ctypes.byref(cb.info), fl, _stream()),
+              "antq_fakequant")
+    return (out, codes) if want_codes else out
+
+
+def fakequant_plan(x, cb, per_row, ovp=False, flags=0):
+    rows, cols = _rows_cols(x, per_row)
+    fl = flags | (_lib.FLAG_OVP if ovp else 0)
+    return lib.antq_fakequant_plan(ctypes.byref(cb.info), rows, cols, _dtype_code(x), fl, _ptr(x), _ptr(x), None)
+
+
+def absmax(x, per_row):
+    _need_cuda(x, "x")
+    with torch.cuda.device(x.device):
+        xc = x.contiguous()
+        rows, cols = _rows_cols(xc, per_row)
+        out = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        check(lib.antq_absmax(_ptr(xc), _ptr(out), rows, cols, _dtype_code(xc), _stream()), "antq_absmax")
+    return out
+
+
+def mse_sweep(x, base_alpha, ratios, cb, per_row, ovp=False):
+    """err[c, r] = sum_row (fakequant(x; alpha = base[r] * ratios[c]) - x)^2  (float64)."""
+    _need_cuda(x, "x")
+    with torch.cuda.device(x.device):
+        xc = x.contiguous()
+        rows, cols = _rows_cols(xc, per_row)
+        a = _alpha_arg(base_alpha, rows, per_row, xc.device)
+        r = ratios.detach().to(device=xc.device, dtype=torch.float32).reshape(-1).contiguous()
+        err = torch.empty((r.numel(), rows), dtype=torch.float64, device=xc.device)
+        check(lib.antq_mse_sweep(_ptr(xc), _ptr(a), int(bool(per_row)), _ptr(r), r.numel(), _ptr(err), rows, cols,
+                                 _dtype_code(xc), _ptr(cb.buf), _lib.FLAG_OVP if ovp else 0, _stream()),
+              "antq_mse_sweep")
+    return err
+
+
+class HostPipeline:
+    """antq_host_*: fake-quant of HOST buffers (H2D, kernel, D2H pipelined in chunks)."""
+
+    def __init__(self, device=0, chunk_bytes=8 << 20, n_stages=3):
+        self._h = ctypes.c_void_p()
+        check(lib.antq_host_create(ctypes.byref(self._h), int(device), int(chunk_bytes), int(n_stages)),
+              "antq_host_create")
+
+    def close(self):
+        if self._h:
+            lib.antq_host_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fakequant(self, x, out, alpha, grid, per_row, outliers=None, ovp=False):
+        """x/out: CPU tensors (ideally pinned), alpha/grid/outliers: CPU fp32 tensors."""
+        for t in (x, out, alpha, grid):
+            if t.is_cuda:
+                raise RuntimeError("HostPipeline takes host tensors")
+        rows, cols = _rows_cols(x, per_row)
+        a = alpha.detach().to(torch.float32).reshape(-1).contiguous()
+        g = grid.detach().to(torch.float32).reshape(-1).contiguous()
+        o = outliers.detach().to(torch.float32).reshape(-1).contiguous() if outliers is not None else None
+        check(lib.antq_host_fakequant(self._h, _ptr(x), _ptr(out), _ptr(a), int(bool(per_row)), rows, cols,
+                                      _dtype_code(x), _ptr(g), g.numel(), _ptr(o), 0 if o is None else o.numel(),
+                                      _lib.FLAG_OVP if ovp else 0), "antq_host_fakequant")
+        return out
+
+    @property
+    def last_launches(self):
+        return lib.antq_host_last_launches(self._h)

@@ -1,0 +1,277 @@
+// antq_capi.cu -- the extern "C" surface declared in include/antq.h: argument
+// checks, kernel selection, and the host-buffer pipeline.  No torch, no C++
+// types across the boundary, no allocation/synchronisation in device entry points.
+#include <new>
+#include <string.h>
+
+#include "antq_common.cuh"
+
+int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
+                     long long cols, int dtype, const AntqCodebook *cb, int nt, bool sym, bool ovp, cudaStream_t st);
+int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
+                     long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
+int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
+int antq_launch_mse_sweep(const void *x, const float *base_alpha, int alpha_per_row, const float *ratios, int n_cand,
+                          double *err, long long rows, long long cols, int dtype, const AntqCodebook *cb, bool ovp,
+                          cudaStream_t st);
+
+namespace {
+inline int esize(int dtype) { return dtype == ANTQ_F32 ? 4 : (dtype == ANTQ_F16 || dtype == ANTQ_BF16) ? 2 : 0; }
+constexpr long long kRowsMinCols = 512;   // below this the per-row prologue costs more than it saves
+}  // namespace
+
+extern "C" {
+
+int antq_abi_version(void) { return ANTQ_ABI_VERSION; }
+
+const char *antq_build_info(void) {
+    return "libantq sm_100a; kernels: antq_prepare_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
+           "antq_mse_sweep_kernel; built " __DATE__;
+}
+
+const char *antq_error_string(int status) {
+    if (status == 0) return "ok";
+    if (status == ANTQ_EINVAL) return "antq: invalid argument";
+    if (status == ANTQ_ENOTSUP) return "antq: unsupported configuration for the requested kernel";
+    if (status == ANTQ_EALIGN) return "antq: pointer not aligned to the element size";
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "antq: unknown error";
+}
+
+size_t antq_codebook_bytes(void) { return sizeof(AntqCodebook); }
+
+int antq_codebook_prepare(const float *grid, int k_normal, const float *outliers, int k_out, void *codebook,
+                          void *stream) {
+    if (!grid || !codebook || k_normal < 1 || k_out < 0 || k_normal + k_out > ANTQ_MAX_GRID) return ANTQ_EINVAL;
+    if (k_out > 0 && !outliers) return ANTQ_EINVAL;
+    return antq_launch_prepare(grid, k_normal, outliers, k_out, (AntqCodebook *)codebook, (cudaStream_t)stream);
+}
+
+int antq_lut_nearest(const void *x, void *z, int16_t *codes, int64_t n, int dtype, const void *codebook,
+                     void *stream) {
+    if (n < 0 || !codebook || esize(dtype) == 0) return ANTQ_EINVAL;
+    if (n == 0) return 0;
+    if (!x || !z) return ANTQ_EINVAL;
+    if ((uintptr_t)x % esize(dtype) || (uintptr_t)z % esize(dtype)) return ANTQ_EALIGN;
+    return antq_launch_flat(x, z, codes, nullptr, 0, 1, n, dtype, (const AntqCodebook *)codebook, false, false,
+                            (cudaStream_t)stream);
+}
+
+int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t cols, int dtype, int flags,
+                        const void *x, const void *out, const void *codes) {
+    const int es = esize(dtype);
+    if (es == 0 || rows < 0 || cols < 0) return ANTQ_EINVAL;
+    if (flags & ANTQ_FLAG_FORCE_FLAT) return 2;
+    const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
+    bool ok = info != nullptr;
+    if (ok) {
+        const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
+        const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+        const int vec = 16 / es;
+        ok = (info->flags & ANTQ_CB_WELLSEP) && (info->flags & ANTQ_CB_STE_EXACT) && nt >= 1 && nt <= 31;
+        ok = ok && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)codes % 16 == 0);
+        ok = ok && (cols % vec == 0 || rows == 1);
+        ok = ok && (!ovp || ((info->flags & ANTQ_CB_OVP_OK) && cols % 2 == 0));
+        ok = ok && (cols >= kRowsMinCols || (flags & ANTQ_FLAG_FORCE_ROWS));
+    }
+    if (ok) return 1;
+    return (flags & ANTQ_FLAG_FORCE_ROWS) ? ANTQ_ENOTSUP : 2;
+}
+
+int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, int64_t rows,
+                   int64_t cols, int dtype, const void *codebook, const antq_codebook_info *info, int flags,
+                   void *stream) {
+    const int es = esize(dtype);
+    if (es == 0 || rows < 0 || cols < 0 || !codebook || !alpha) return ANTQ_EINVAL;
+    if (rows == 0 || cols == 0) return 0;
+    if (!x || !out) return ANTQ_EINVAL;
+    if ((uintptr_t)x % es || (uintptr_t)out % es || (uintptr_t)codes % 2) return ANTQ_EALIGN;
+    const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
+    if (ovp && x == out && ((rows * cols) & 1)) return ANTQ_EINVAL;   // wrap-around pair reads x[0]
+    const int plan = antq_fakequant_plan(info, rows, cols, dtype, flags, x, out, codes);
+    if (plan < 0) return plan;
+    const AntqCodebook *cb = (const AntqCodebook *)codebook;
+    if (plan == 1) {
+        const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
+        const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+        return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, nt, sym, ovp,
+                                (cudaStream_t)stream);
+    }
+    return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp,
+                            (cudaStream_t)stream);
+}
+
+int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype, void *stream) {
+    const int es = esize(dtype);
+    if (es == 0 || rows < 0 || cols < 0 || !out) return ANTQ_EINVAL;
+    if (rows * cols > 0 && !x) return ANTQ_EINVAL;
+    if ((uintptr_t)x % es) return ANTQ_EALIGN;
+    return antq_launch_absmax(x, out, rows, cols, dtype, (cudaStream_t)stream);
+}
+
+int antq_mse_sweep(const void *x, const float *base_alpha, int alpha_per_row, const float *ratios, int n_cand,
+                   double *err, int64_t rows, int64_t cols, int dtype, const void *codebook, int flags,
+                   void *stream) {
+    const int es = esize(dtype);
+    if (es == 0 || rows < 0 || cols < 0 || n_cand < 0 || !codebook || !base_alpha || !ratios || !err)
+        return ANTQ_EINVAL;
+    if (rows * cols > 0 && !x) return ANTQ_EINVAL;
+    if ((uintptr_t)x % es) return ANTQ_EALIGN;
+    const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
+    if (ovp && (cols & 1) && rows > 1) return ANTQ_ENOTSUP;
+    return antq_launch_mse_sweep(x, base_alpha, alpha_per_row, ratios, n_cand, err, rows, cols, dtype,
+                                 (const AntqCodebook *)codebook, ovp, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------
+// Host-buffer pipeline: H2D -> fused kernel -> D2H in row chunks over n_stages streams.
+// ---------------------------------------------------------------------------------
+struct antq_host_ctx {
+    int device;
+    size_t chunk_bytes;
+    int n_stages;
+    cudaStream_t st[8];
+    void *d_in[8];
+    void *d_out[8];
+    AntqCodebook *cb;
+    float *d_grid;          // ANTQ_MAX_GRID floats
+    float *d_alpha;
+    size_t alpha_cap;
+    float h_grid[ANTQ_MAX_GRID];
+    int h_k_normal, h_k_out;
+    antq_codebook_info info;
+    int last_launches;
+};
+
+int antq_host_create(antq_host_ctx **out, int device, size_t chunk_bytes, int n_stages) {
+    if (!out || n_stages < 1 || n_stages > 8 || chunk_bytes < 4096) return ANTQ_EINVAL;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    antq_host_ctx *c = new (std::nothrow) antq_host_ctx();
+    if (!c) return (int)cudaErrorMemoryAllocation;
+    memset(c, 0, sizeof(*c));
+    c->device = device; c->chunk_bytes = chunk_bytes; c->n_stages = n_stages; c->h_k_normal = -1;
+    for (int i = 0; i < n_stages && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_in[i], chunk_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_out[i], chunk_bytes);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->cb, sizeof(AntqCodebook));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_grid, sizeof(float) * ANTQ_MAX_GRID);
+    if (e != cudaSuccess) { antq_host_destroy(c); return (int)e; }
+    *out = c;
+    return 0;
+}
+
+void antq_host_destroy(antq_host_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 8; i++) {
+        if (c->st[i]) { cudaStreamSynchronize(c->st[i]); cudaStreamDestroy(c->st[i]); }
+        if (c->d_in[i]) cudaFree(c->d_in[i]);
+        if (c->d_out[i]) cudaFree(c->d_out[i]);
+    }
+    if (c->cb) cudaFree(c->cb);
+    if (c->d_grid) cudaFree(c->d_grid);
+    if (c->d_alpha) cudaFree(c->d_alpha);
+    delete c;
+}
+
+int antq_host_last_launches(const antq_host_ctx *c) { return c ? c->last_launches : 0; }
+
+int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, const float *alpha_host,
+                        int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
+                        int k_normal, const float *outliers_host, int k_out, int flags) {
+    const int es = esize(dtype);
+    if (!c || es == 0 || rows < 0 || cols < 0 || !alpha_host || !grid_host) return ANTQ_EINVAL;
+    if (k_normal < 1 || k_out < 0 || k_normal + k_out > ANTQ_MAX_GRID || (k_out > 0 && !outliers_host))
+        return ANTQ_EINVAL;
+    c->last_launches = 0;
+    if (rows == 0 || cols == 0) return 0;
+    if (!x_host || !out_host) return ANTQ_EINVAL;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t s0 = c->st[0];
+
+    // codebook: rebuild only when the grid changed
+    float g[ANTQ_MAX_GRID];
+    memset(g, 0, sizeof(g));
+    memcpy(g, grid_host, sizeof(float) * k_normal);
+    if (k_out) memcpy(g + k_normal, outliers_host, sizeof(float) * k_out);
+    if (c->h_k_normal != k_normal || c->h_k_out != k_out || memcmp(g, c->h_grid, sizeof(g)) != 0) {
+        e = cudaMemcpyAsync(c->d_grid, g, sizeof(g), cudaMemcpyHostToDevice, s0);
+        if (e != cudaSuccess) return (int)e;
+        int rc = antq_launch_prepare(c->d_grid, k_normal, c->d_grid + k_normal, k_out, c->cb, s0);
+        if (rc) return rc;
+        c->last_launches++;
+        rc = antq_codebook_info_get(c->cb, &c->info, s0);
+        if (rc) return rc;
+        c->last_launches++;
+        memcpy(c->h_grid, g, sizeof(g));
+        c->h_k_normal = k_normal; c->h_k_out = k_out;
+    }
+    // alpha
+    const size_t n_alpha = alpha_per_row ? (size_t)rows : 1;
+    if (c->alpha_cap < n_alpha) {
+        if (c->d_alpha) cudaFree(c->d_alpha);
+        c->d_alpha = nullptr; c->alpha_cap = 0;
+        e = cudaMalloc((void **)&c->d_alpha, sizeof(float) * n_alpha);
+        if (e != cudaSuccess) return (int)e;
+        c->alpha_cap = n_alpha;
+    }
+    e = cudaMemcpyAsync(c->d_alpha, alpha_host, sizeof(float) * n_alpha, cudaMemcpyHostToDevice, s0);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(s0);       // alpha + codebook visible to every stage stream
+    if (e != cudaSuccess) return (int)e;
+
+    const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
+    const size_t row_bytes = (size_t)cols * es;
+    int rc = 0;
+    int stage = 0;
+    if (alpha_per_row && rows > 1) {
+        if (row_bytes > c->chunk_bytes) return ANTQ_ENOTSUP;
+        if (ovp && (cols & 1)) return ANTQ_ENOTSUP;     // pairs would straddle chunk boundaries
+        const int64_t rpc = (int64_t)(c->chunk_bytes / row_bytes);
+        for (int64_t r0 = 0; r0 < rows && rc == 0; r0 += rpc, stage = (stage + 1) % c->n_stages) {
+            const int64_t nr = (rows - r0) < rpc ? (rows - r0) : rpc;
+            const size_t bytes = (size_t)nr * row_bytes;
+            cudaStream_t st = c->st[stage];
+            e = cudaMemcpyAsync(c->d_in[stage], (const char *)x_host + (size_t)r0 * row_bytes, bytes,
+                                cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { rc = (int)e; break; }
+            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha + r0, 1, nr, cols, dtype, c->cb,
+                                &c->info, flags, st);
+            if (rc) break;
+            c->last_launches++;
+            e = cudaMemcpyAsync((char *)out_host + (size_t)r0 * row_bytes, c->d_out[stage], bytes,
+                                cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = (int)e;
+        }
+    } else {
+        const int64_t n = rows * cols;
+        int64_t epc = (int64_t)(c->chunk_bytes / es) & ~(int64_t)63;   // even, vector aligned
+        if (ovp && (n & 1) && n > epc) return ANTQ_ENOTSUP;            // wrap-around pair needs one launch
+        for (int64_t i0 = 0; i0 < n && rc == 0; i0 += epc, stage = (stage + 1) % c->n_stages) {
+            const int64_t ne = (n - i0) < epc ? (n - i0) : epc;
+            const size_t bytes = (size_t)ne * es;
+            cudaStream_t st = c->st[stage];
+            e = cudaMemcpyAsync(c->d_in[stage], (const char *)x_host + (size_t)i0 * es, bytes, cudaMemcpyHostToDevice,
+                                st);
+            if (e != cudaSuccess) { rc = (int)e; break; }
+            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha, 0, 1, ne, dtype, c->cb, &c->info,
+                                flags, st);
+            if (rc) break;
+            c->last_launches++;
+            e = cudaMemcpyAsync((char *)out_host + (size_t)i0 * es, c->d_out[stage], bytes, cudaMemcpyDeviceToHost,
+                                st);
+            if (e != cudaSuccess) rc = (int)e;
+        }
+    }
+    for (int i = 0; i < c->n_stages; i++) {
+        e = cudaStreamSynchronize(c->st[i]);
+        if (e != cudaSuccess && rc == 0) rc = (int)e;
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// antq_prepare.cu -- build the device codebook from the reference's `quant_grid`
+// (+ OliVe `outliers`) buffers.  One CTA, K <= 512 threads, no host round trip.
+//
+// The reference scan (A/quant/quant_kernel.cu:25-37) walks the grid in order and
+// keeps the LAST entry with the smallest fl32(|d - g_i|).  For two adjacent
+// distinct values lo < hi the predicate "hi beats lo" is monotone in d, because
+// fl32(|d - hi|) is non-increasing and fl32(|d - lo|) non-decreasing on [lo, hi]
+// (rounding is monotone).  So an exact fp32 threshold thr = min{d : hi wins}
+// exists; it is found here by bisection over the fp32 number line using the
+// scan's own rounded distances and its tie rule (later scan index wins).
+// rank(d) = #{r : d >= thr[r]} then names the level the scan returns, provided
+// no NON-adjacent level can tie with the winner -- checked below (WELLSEP).
+#include "antq_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool hi_wins(float d, float lo, float hi, bool tie_hi) {
+    float dl = fabsf(__fsub_rn(d, lo));
+    float dh = fabsf(__fsub_rn(d, hi));
+    return dh < dl || (dh == dl && tie_hi);
+}
+
+__global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float *__restrict__ grid, int k_normal,
+                                                                     const float *__restrict__ outliers, int k_out,
+                                                                     AntqCodebook *__restrict__ cb) {
+    __shared__ float g[ANTQ_MAX_GRID];
+    __shared__ int keep[ANTQ_MAX_GRID];   // 1 if entry i is the last occurrence of its value
+    __shared__ float lev[ANTQ_MAX_GRID];
+    __shared__ int lcode[ANTQ_MAX_GRID];
+    __shared__ float thr[ANTQ_MAX_GRID];
+    __shared__ int s_nlev, s_flags_bad_sep, s_flags_bad_ste, s_sym_bad, s_ovp_bad;
+    __shared__ float s_gmax;
+
+    const int K = k_normal + k_out;
+    const int i = threadIdx.x;
+    if (i == 0) {
+        s_nlev = 0; s_flags_bad_sep = 0; s_flags_bad_ste = 0; s_sym_bad = 0; s_ovp_bad = 0;
+        float m = k_normal > 0 ? grid[0] : 0.0f;        // torch.max(self.quant_grid)
+        for (int j = 1; j < k_normal; j++) m = (grid[j] > m || grid[j] != grid[j]) ? grid[j] : m;
+        s_gmax = m;
+    }
+    float gi = 0.0f;
+    if (i < K) {
+        gi = i < k_normal ? grid[i] : outliers[i - k_normal];
+        g[i] = gi;
+    }
+    __syncthreads();
+
+    // distinct values: keep the LAST occurrence (it is the one the `<=` scan returns); drop NaN.
+    int my_keep = 0;
+    if (i < K && gi == gi) {
+        my_keep = 1;
+        for (int j = i + 1; j < K; j++)
+            if (g[j] == gi) my_keep = 0;
+    }
+    if (i < K) keep[i] = my_keep;
+    __syncthreads();
+    if (my_keep) {
+        int r = 0;
+        for (int j = 0; j < K; j++)
+            if (keep[j] && g[j] < gi) r++;
+        lev[r] = (gi == 0.0f) ? 0.0f : gi;   // canonical +0
+        lcode[r] = i;
+        atomicAdd(&s_nlev, 1);
+    }
+    __syncthreads();
+    const int L = s_nlev;
+
+    // thresholds between adjacent levels
+    if (i < L - 1) {
+        float lo = lev[i], hi = lev[i + 1];
+        bool tie_hi = lcode[i + 1] > lcode[i];
+        long long a = antq_f2ord(lo), b = antq_f2ord(hi);   // hi_wins(lo) is false, hi_wins(hi) is true
+        while (b - a > 1) {
+            long long m = (a + b) >> 1;
+            if (hi_wins(antq_ord2f((int)m), lo, hi, tie_hi)) b = m; else a = m;
+        }
+        float t = antq_ord2f((int)b);
+        thr[i] = t;
+        // (q - d) + d == q inside the span: |q - d| <= min(|q|, |d|) or q == 0  (Sterbenz)
+        bool lo_ok = lo == 0.0f || (lo > 0.0f && t <= 2.0f * lo) || (lo < 0.0f && t <= 0.5f * lo);
+        bool hi_ok = hi == 0.0f || (hi < 0.0f && t >= 2.0f * hi) || (hi > 0.0f && t >= 0.5f * hi);
+        if (!(lo_ok && hi_ok)) s_flags_bad_ste = 1;
+        // a non-adjacent level can only tie with the winner if two gaps differ by > 2^22
+        if (i < L - 2) {
+            float span = lev[i + 2] - lo;
+            if (!((hi - lo) > span * 4.8e-7f) || !((lev[i + 2] - hi) > span * 4.8e-7f)) s_flags_bad_sep = 1;
+        }
+    }
+    __syncthreads();
+
+    if (i == 0) {
+        const float vmax = L > 0 ? lev[L - 1] : 0.0f, vmin = L > 0 ? lev[0] : 0.0f;
+        int flags = 0;
+        // beyond the ends the winner is the extreme level as long as the runner-up cannot tie:
+        // gaps at both ends must exceed the fp32 resolution at the largest window we use.
+        bool sep = !s_flags_bad_sep && L >= 1 && fabsf(vmax) <= 4096.0f && fabsf(vmin) <= 4096.0f;
+        if (L >= 2) {
+            if (!((lev[L - 1] - lev[L - 2]) > 0.02f) && lcode[L - 2] > lcode[L - 1]) sep = false;
+            if (!((lev[1] - lev[0]) > 0.02f) && lcode[1] > lcode[0]) sep = false;
+        }
+        if (sep) flags |= ANTQ_CB_WELLSEP;
+        bool ste = !s_flags_bad_ste && vmax > 0.0f && vmin <= 0.0f;
+        if (ste) flags |= ANTQ_CB_STE_EXACT;
+        // symmetric about a zero level?
+        bool sym = (L & 1) && L >= 3;
+        int mid = L >> 1;
+        if (sym) {
+            if (lev[mid] != 0.0f) sym = false;
+            for (int k = 1; sym && k <= mid; k++)
+                if (lev[mid + k] != -lev[mid - k]) sym = false;
+        }
+        if (sym) flags |= ANTQ_CB_SYMMETRIC;
+        // OVP: outliers are levels with |v| > 32 (O/antquant/quant_modules.py:314)
+        int ovp_index = -1;
+        bool ovp_ok = true;
+        if (sym) {
+            for (int k = 0; k <= mid; k++)
+                if (fabsf(lev[mid + k]) > 32.0f) { ovp_index = k - 1; break; }
+        } else {
+            for (int r = 0; r < L; r++) {
+                if (lev[r] < -32.0f) ovp_ok = false;            // negative outliers need the symmetric path
+                if (lev[r] > 32.0f && ovp_index < 0) ovp_index = r - 1;
+            }
+        }
+        if (ovp_index < 0 && !sym) { /* no outlier level at all: OVP is a no-op */ }
+        if (ovp_ok) flags |= ANTQ_CB_OVP_OK;
+
+        cb->n_entries = K;
+        cb->n_normal = k_normal;
+        cb->n_levels = L;
+        cb->flags = flags;
+        cb->n_mag = sym ? mid + 1 : 0;
+        cb->mid = sym ? mid : 0;
+        cb->ovp_index = ovp_index;
+        cb->gmax = s_gmax;
+        cb->vmax = vmax;
+        cb->vmin = vmin;
+        // window in which clipped values still satisfy (q - d) + d == q  (|d| <= 2 |q|);
+        // an unsigned grid (vmin == 0) is limited by its positive end only.
+        float lim_pos = 2.0f * vmax;
+        float lim_neg = vmin < 0.0f ? -2.0f * vmin : lim_pos;
+        float lim = lim_pos < lim_neg ? lim_pos : lim_neg;
+        cb->lim = lim < 65536.0f ? lim : 65536.0f;
+        cb->magic = ANTQ_CB_MAGIC;
+    }
+    if (i < ANTQ_MAX_GRID) {
+        cb->grid[i] = i < K ? g[i] : 0.0f;
+        cb->level[i] = i < L ? lev[i] : 0.0f;
+        cb->level_code[i] = i < L ? lcode[i] : ANTQ_CODE_NONE;
+        cb->thr[i] = i < L - 1 ? thr[i] : __int_as_float(0x7f800000);
+    }
+    // symmetric magnitude thresholds
+    if (i < ANTQ_MAX_GRID / 2) {
+        int mid = L >> 1;
+        float tp = __int_as_float(0x7f800000), tn = tp;
+        if ((L & 1) && i < mid) {
+            tp = thr[mid + i];
+            // negative side: -m_{i+1} is chosen while d < thr[mid-i-1], i.e. -d >= nextup(-thr)
+            float nt = -thr[mid - i - 1];
+            tn = antq_ord2f(antq_f2ord(nt) + 1);
+        }
+        cb->mag_tpos[i] = tp;
+        cb->mag_tneg[i] = tn;
+    }
+}
+
+__global__ void antq_cb_info_kernel(const AntqCodebook *__restrict__ cb, antq_codebook_info *__restrict__ out) {
+    out->n_entries = cb->n_entries; out->n_normal = cb->n_normal; out->n_levels = cb->n_levels;
+    out->flags = cb->flags; out->n_mag = cb->n_mag; out->mid = cb->mid; out->ovp_index = cb->ovp_index;
+    out->reserved = cb->magic;
+    out->gmax = cb->gmax; out->vmax = cb->vmax; out->vmin = cb->vmin; out->lim = cb->lim;
+}
+
+}  // namespace
+
+int antq_launch_prepare(const float *grid, int k_normal, const float *outliers, int k_out, AntqCodebook *cb,
+                        cudaStream_t stream) {
+    antq_prepare_kernel<<<1, ANTQ_MAX_GRID, 0, stream>>>(grid, k_normal, outliers, k_out, cb);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, void *stream) {
+    if (!codebook || !info_host) return ANTQ_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    antq_codebook_info *tmp = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&tmp, sizeof(antq_codebook_info), st);
+    if (e != cudaSuccess) return (int)e;
+    antq_cb_info_kernel<<<1, 1, 0, st>>>((const AntqCodebook *)codebook, tmp);
+    e = cudaMemcpyAsync(info_host, tmp, sizeof(antq_codebook_info), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(tmp, st);
+    return (int)e;
+}

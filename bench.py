@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- quant-dequant throughput of the ANT/OliVe fake-quant forward on B200.
+
+Metric (BASELINE.json): quant-dequant GB/s of ALGORITHMIC bytes (and % of measured HBM
+peak) on 4096x4096 fp16 -> 4-bit flint -> fp16, per-output-channel scale (the OPT-6.7B
+attention weight).  A "step" is one pass of the hot path over a batch of
+NB = 8 distinct 4096x4096 tensors (8 launches, 537 MB touched > the 126 MB L2, so every
+launch streams from HBM).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference path on host cores
+
+Multi-GPU (torchrun, one rank per GPU): the path shards by tensor with no data-path
+collective, so scaling is "weak" -- every rank runs its own batch; value = all bytes / max-rank time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "ant-quantization_b200"))
+
+N, NB = 4096, 8                 # tensor side, tensors per step
+BYTES_PER_ELEM = 4              # fp16 in + fp16 out
+WORKLOAD = "opt6.7b-attn-weight 4096x4096 fp16 -> flint-4 (signed, per-channel alpha) -> fp16, 8 tensors/step"
+METRIC = "quant-dequant GB/s (% HBM peak), 4096x4096 fp16->4b flint"
+NCU_TRAFFIC_BYTES = None        # dram read+write per launch from profiles/ (ncu --set full); None until captured
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            p = [c.strip() for c in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def flint4_grid():
+    """The signed 4-bit flint codebook (reference: A/antquant/quant_modules.py:223-278)."""
+    from antq.codebooks import ant_grid
+    return ant_grid("flint", 4, True)
+
+
+def make_inputs(torch, device, nb, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xs, alphas = [], []
+    for _ in range(nb):
+        x = (torch.randn(N, N, generator=g) * 0.02).to(torch.float16)       # weights-like
+        alphas.append((x.float().abs().amax(1) * 0.9).contiguous())
+        xs.append(x)
+    return xs, alphas
+
+
+def cpu_reference_leg(seconds_target=10.0, rows=None):
+    """The reference path restated on the CPU (oracle/, 'port'): literal scan + fp32 arithmetic,
+    OpenMP over rows.  Bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import antq_oracle as orc
+    rows = rows or N
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((rows, N)) * 0.02).astype(np.float16)
+    alpha = (np.abs(x.astype(np.float32)).max(1) * 0.9).astype(np.float32)
+    grid = orc.ant_grid("flint", 4, True)
+    orc.ant_forward(x[:64], alpha[:64], grid, per_row=True)                 # build + warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        orc.ant_forward(x, alpha, grid, per_row=True)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds_target or reps >= 50:
+            break
+    gbs = reps * rows * N * BYTES_PER_ELEM / dt / 1e9
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": "%d x (%dx%d fp16 flint-4 per-channel), oracle/antq_oracle.c literal scan, OpenMP, %.1f s"
+                      % (reps, rows, N, dt)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import antq_oracle as orc
+    rows = 1024                                         # bounded sample: a quarter tensor per step
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((rows, N)) * 0.02).astype(np.float16)
+    alpha = (np.abs(x.astype(np.float32)).max(1) * 0.9).astype(np.float32)
+    grid = orc.ant_grid("flint", 4, True)
+    for _ in range(max(args.warmup, 1)):
+        orc.ant_forward(x, alpha, grid, per_row=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.ant_forward(x, alpha, grid, per_row=True)
+    dt = time.perf_counter() - t0
+    gbs = args.steps * rows * N * BYTES_PER_ELEM / dt / 1e9
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    sample = "%d steps x (%dx%d fp16 flint-4 per-channel) on %d host threads" % (args.steps, rows, N, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample,
+                       "note": "the reference has no CPU kernel (quant.cpp calls CUDA unconditionally); this is its "
+                               "algorithm restated in C (oracle/), all host threads"},
+            "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import antq
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fake-quant path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    cb = antq.prepare_codebook(flint4_grid().to(device))
+    xs_h, alphas_h = make_inputs(torch, device, NB, seed=1234 + rank)
+    xs = [x.to(device) for x in xs_h]
+    alphas = [a.to(device) for a in alphas_h]
+    outs = [torch.empty_like(x) for x in xs]
+    assert antq.fakequant_plan(xs[0], cb, True) == 1, "row-table kernel not selected"
+
+    def step():
+        for i in range(NB):
+            antq.fakequant(xs[i], alphas[i], cb, True, out=outs[i])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.12)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    step_bytes = NB * N * N * BYTES_PER_ELEM
+    value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
+    launch_us = ms * 1e3 / (args.steps * NB)
+    achieved = N * N * BYTES_PER_ELEM / (launch_us * 1e-6) / 1e9
+    peak, peak_src = hbm_peak()
+
+    # ---- end to end: HOST (pinned) buffers through the C-ABI host entry point ----
+    e2e = None
+    if not args.no_e2e:
+        hp = antq.HostPipeline(device=local, chunk_bytes=8 << 20, n_stages=3)
+        xp = [x.pin_memory() for x in xs_h]
+        op = [torch.empty_like(x).pin_memory() for x in xs_h]
+        grid_h = flint4_grid()
+        e2e_steps = max(3, min(args.steps, 10))
+        launches_e2e = 0
+
+        def e2e_step():
+            n = 0
+            for i in range(NB):
+                hp.fakequant(xp[i], op[i], alphas_h[i], grid_h, per_row=True)
+                n += hp.last_launches
+            return n
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            launches_e2e += e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(world * step_bytes * e2e_steps / dt / 1e9, 3), "unit": "GB/s",
+               "h2d_bytes_per_step": NB * N * N * 2 + NB * N * 4, "d2h_bytes_per_step": NB * N * N * 2,
+               "steps": e2e_steps, "api": "antq_host_fakequant (C ABI, pinned host buffers, 3-stage 8 MiB chunks)"}
+        hp.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cpu = cpu_reference_leg()
+        except Exception as e:      # the oracle is test infrastructure; never let it break the GPU number
+            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": N, "cols": N, "tensors_per_step": NB,
+                   "l2_policy": "8 distinct tensor pairs rotate (537 MB per step > 126 MB L2)",
+                   "parallelism": "independent tensors per rank, no collective" if world > 1 else "single GPU",
+                   "pct_of_hbm_peak": round(100.0 * value / world / peak, 2)},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES,
+                     "kernel": "antq_rows_kernel<__half,7,SYM>", "launch_us": round(launch_us, 3),
+                     "algorithmic_bytes_per_launch": N * N * BYTES_PER_ELEM, "peak_source": peak_src},
+        "e2e": e2e, "gpu_launches": args.steps * NB, "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

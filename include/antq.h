@@ -1,0 +1,134 @@
+/*
+ * antq.h -- C ABI of libantq.so: the B200 (sm_100a) fake-quant forward of
+ * ANT / OliVe.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * What each entry point replaces in the reference (A/ = ant_quantization/,
+ * O/ = olive_quantization/ of clevercool/ANT-Quantization @ bc84067):
+ *
+ *   antq_lut_nearest        quant_cuda.quant(x, y)            A/quant/quant.cpp:16-28,
+ *                                                             A/quant/quant_kernel.cu:11-62
+ *   antq_codebook_prepare   (new) turns the `quant_grid` (+`outliers`) buffers
+ *                           A/antquant/quant_modules.py:42, O/antquant/quant_modules.py:44-45
+ *                           into the device codebook the fused kernels read
+ *   antq_fakequant          Quantizer._forward               A/antquant/quant_modules.py:535-551
+ *                           OliVe Quantizer._forward + OVP   O/antquant/quant_modules.py:295-330
+ *   antq_absmax             the abs-max alpha init           A/antquant/quant_modules.py:473-477
+ *   antq_mse_sweep          search_mse's candidate loop      A/antquant/quant_modules.py:287-326,
+ *                                                             O/antquant/quant_modules.py:190-233
+ *   antq_host_*             the same forward for HOST buffers (copies inside)
+ *
+ * Conventions
+ *   - every device entry point is asynchronous on `stream`, never allocates,
+ *     never synchronises, never throws; it returns 0 on success, a positive
+ *     cudaError_t, or a negative ANTQ_E* argument error.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - all pointers are device pointers unless the name ends in `_host`.
+ *   - tensors are contiguous, viewed as [rows, cols]; per-tensor scale is
+ *     rows = 1, cols = numel.  alpha is fp32, one value per row
+ *     (alpha_per_row = 1) or a single value (alpha_per_row = 0).
+ *   - dtype is the I/O element type; arithmetic is fp32 exactly as in the
+ *     reference; fp16/bf16 results are the fp32 result rounded to nearest even.
+ */
+#ifndef ANTQ_H
+#define ANTQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANTQ_ABI_VERSION 1
+#define ANTQ_MAX_GRID 512           /* entries in grid + outliers */
+
+/* dtype */
+#define ANTQ_F32  0
+#define ANTQ_F16  1
+#define ANTQ_BF16 2
+
+/* flags for antq_fakequant */
+#define ANTQ_FLAG_OVP        1      /* OliVe outlier-victim pair masking on the flat tensor */
+#define ANTQ_FLAG_FORCE_FLAT 2      /* testing: always take the generic flat kernel */
+#define ANTQ_FLAG_FORCE_ROWS 4      /* testing: fail (ANTQ_ENOTSUP) instead of falling back */
+
+/* argument errors (negative); positive return values are cudaError_t */
+#define ANTQ_EINVAL  (-1)
+#define ANTQ_ENOTSUP (-2)
+#define ANTQ_EALIGN  (-3)
+
+/* codes written by the kernels: index into the (concatenated) grid of the
+ * entry the reference scan selects (last minimal entry), or one of: */
+#define ANTQ_CODE_NONE   (-1)       /* no entry within 102400 / NaN / Inf: the scan keeps z = 0 */
+/* victims of the OVP mask get code == number of grid entries */
+
+int antq_abi_version(void);
+const char *antq_build_info(void);
+const char *antq_error_string(int status);
+
+/* Bytes of device memory one codebook occupies. */
+size_t antq_codebook_bytes(void);
+
+/* Build the codebook on the device from device-resident grid buffers.
+ * grid: k_normal fp32 entries (the `quant_grid` buffer); outliers: k_out fp32
+ * entries or NULL/0 (the OliVe `outliers` buffer).  The scan order is
+ * grid then outliers, as torch.cat does (O/antquant/quant_modules.py:304). */
+int antq_codebook_prepare(const float *grid, int k_normal, const float *outliers, int k_out,
+                          void *codebook, void *stream);
+
+/* z[i] = grid entry the reference scan selects for x[i]; codes optional (int16). */
+int antq_lut_nearest(const void *x, void *z, int16_t *codes, int64_t n, int dtype,
+                     const void *codebook, void *stream);
+
+/* Introspection: copy the prepared codebook's header to the host.  This is the ONE
+ * synchronising call of the device API (it waits for `stream`); call it once after
+ * antq_codebook_prepare and keep the result next to the codebook pointer. */
+typedef struct antq_codebook_info {
+    int32_t n_entries, n_normal, n_levels, flags, n_mag, mid, ovp_index, reserved;
+    float gmax, vmax, vmin, lim;
+} antq_codebook_info;
+int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, void *stream);
+
+#define ANTQ_CB_WELLSEP   1   /* threshold search is provably equal to the scan */
+#define ANTQ_CB_STE_EXACT 2   /* (q - d) + d == q inside the window |d| <= lim */
+#define ANTQ_CB_SYMMETRIC 4   /* levels symmetric about a zero level */
+#define ANTQ_CB_OVP_OK    8   /* no outlier level (|v| > 32) on the negative side of an asymmetric grid */
+
+/* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
+ * `info` (host pointer, may be NULL) lets the call pick the row-table kernel
+ * without touching device memory; with NULL the generic flat kernel runs. */
+int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row,
+                   int64_t rows, int64_t cols, int dtype, const void *codebook,
+                   const antq_codebook_info *info, int flags, void *stream);
+
+/* Which kernel antq_fakequant launches for these arguments:
+ * 1 = row-table kernel (x-space thresholds), 2 = flat generic kernel, <0 = error. */
+int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t cols, int dtype, int flags,
+                        const void *x, const void *out, const void *codes);
+
+/* out[r] = max_c |x[r, c]| as fp32 (rows = 1: whole tensor). */
+int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype, void *stream);
+
+/* For every candidate c in [0, n_cand): alpha_c[r] = base[r] * ratio[c]; err[c, r] =
+ * sum_c (fakequant(x)[r, c] - x[r, c])^2 accumulated in fp32 per thread, fp64 across
+ * threads.  One read of x per CAND_TILE candidates. */
+int antq_mse_sweep(const void *x, const float *base_alpha, int alpha_per_row, const float *ratios, int n_cand,
+                   double *err, int64_t rows, int64_t cols, int dtype, const void *codebook, int flags,
+                   void *stream);
+
+/* ---- host-buffer path (what a CPU caller of the reference would use) ---- */
+typedef struct antq_host_ctx antq_host_ctx;
+/* Creates streams, staging buffers (chunk_bytes per direction per stage) on `device`. */
+int antq_host_create(antq_host_ctx **ctx, int device, size_t chunk_bytes, int n_stages);
+void antq_host_destroy(antq_host_ctx *ctx);
+/* Synchronous: returns when out_host is complete.  x_host/out_host should be pinned. */
+int antq_host_fakequant(antq_host_ctx *ctx, const void *x_host, void *out_host, const float *alpha_host,
+                        int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
+                        int k_normal, const float *outliers_host, int k_out, int flags);
+/* Kernels launched by the most recent antq_host_fakequant call. */
+int antq_host_last_launches(const antq_host_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANTQ_H */
