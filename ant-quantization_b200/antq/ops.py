@@ -98,27 +98,46 @@ def _rows_cols(x, per_row):
 
 
 def _alpha_arg(alpha, rows, per_row, device):
-    a = alpha.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    a = alpha
+    if not (a.dtype is torch.float32 and a.device == device and a.is_contiguous() and not a.requires_grad):
+        a = alpha.detach().to(device=device, dtype=torch.float32).contiguous()
     if a.numel() != (rows if per_row else 1):
         raise ValueError("antq: alpha has %d entries, expected %d" % (a.numel(), rows if per_row else 1))
     return a
 
 
+class _maybe_guard:
+    """torch.cuda.device(...) only when the tensor is not on the current device (saves ~10 us per call)."""
+
+    def __init__(self, device):
+        self.g = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.g is not None:
+            self.g.__enter__()
+
+    def __exit__(self, *exc):
+        if self.g is not None:
+            self.g.__exit__(*exc)
+
+
 def fakequant(x, alpha, cb, per_row, ovp=False, want_codes=False, flags=0, out=None):
     """Fused scale -> nearest -> (OVP) -> STE -> rescale.  x: contiguous CUDA tensor;
-    alpha: fp32 CUDA tensor with x.shape[0] entries (per_row) or one entry."""
+    alpha: fp32 CUDA tensor with x.shape[0] entries (per_row) or one entry.
+    No allocation when `out` is given, no synchronisation: safe under CUDA-graph capture."""
     _need_cuda(x, "x")
     if not x.is_contiguous():
         raise RuntimeError("antq: x must be contiguous")
-    with torch.cuda.device(x.device):
+    with _maybe_guard(x.device):
         rows, cols = _rows_cols(x, per_row)
         a = _alpha_arg(alpha, rows, per_row, x.device)
         if out is None:
             out = torch.empty_like(x)
         codes = torch.empty(x.shape, dtype=torch.int16, device=x.device) if want_codes else None
         fl = flags | (_lib.FLAG_OVP if ovp else 0)
-        check(lib.antq_fakequant(_ptr(x), _ptr(out), _ptr(codes), _ptr(a), int(bool(per_row)), rows, cols,
-                                 _dtype_code(x), _ptr(cb.buf), ctypes.byref(cb.info), fl, _stream()),
+        check(lib.antq_fakequant(x.data_ptr(), out.data_ptr(), codes.data_ptr() if want_codes else None,
+                                 a.data_ptr(), int(bool(per_row)), rows, cols, _dtype_code(x), cb.buf.data_ptr(),
+                                 ctypes.byref(cb.info), fl, torch.cuda.current_stream().cuda_stream),
               "antq_fakequant")
     return (out, codes) if want_codes else out
 

@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
         return OUT
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(_compile, SOURCES))
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "--cudart=static", "-o", OUT] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

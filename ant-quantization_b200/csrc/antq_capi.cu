@@ -82,9 +82,9 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
                    int64_t cols, int dtype, const void *codebook, const antq_codebook_info *info, int flags,
                    void *stream) {
     const int es = esize(dtype);
-    if (es == 0 || rows < 0 || cols < 0 || !codebook || !alpha) return ANTQ_EINVAL;
+    if (es == 0 || rows < 0 || cols < 0) return ANTQ_EINVAL;
     if (rows == 0 || cols == 0) return 0;
-    if (!x || !out) return ANTQ_EINVAL;
+    if (!x || !out || !codebook || !alpha) return ANTQ_EINVAL;
     if ((uintptr_t)x % es || (uintptr_t)out % es || (uintptr_t)codes % 2) return ANTQ_EALIGN;
     const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
     if (ovp && x == out && ((rows * cols) & 1)) return ANTQ_EINVAL;   // wrap-around pair reads x[0]

@@ -29,7 +29,9 @@ struct AntqCodebook {
     int32_t magic;
     float gmax;          // max(quant_grid): the reference's scale denominator
     float vmax, vmin;    // extreme levels
-    float lim;           // window |d| <= lim in which (q - d) + d == q and the threshold search == scan
+    float lim;           // window |d| <= lim in which (q - d) + d == q AND the threshold search == scan
+    float lim_idx;       // window |d| <= lim_idx in which the threshold search == scan (no STE claim)
+    float pad_[3];
     float grid[ANTQ_MAX_GRID];          // scan order (for the literal slow path)
     float level[ANTQ_MAX_GRID];         // sorted distinct values (+0 canonical)
     int32_t level_code[ANTQ_MAX_GRID];  // scan index of each level (last occurrence)

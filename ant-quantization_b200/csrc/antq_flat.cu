@@ -22,10 +22,10 @@ struct Quantized {
 };
 
 __device__ __forceinline__ Quantized antq_quantize_d(const AntqCodebook *__restrict__ cb, const float *s_thr,
-                                                     const float *s_lev, int nlev, bool fast, float d,
+                                                     const float *s_lev, int nlev, float win, float d,
                                                      bool want_code) {
     Quantized r;
-    if (fast && fabsf(d) <= 65536.0f) {
+    if (fabsf(d) <= win) {      // win < 0 disables the threshold search (codebook not well separated)
         const int rank = antq_rank(s_thr, nlev - 1, d);
         r.q = s_lev[rank];
         r.code = want_code ? cb->level_code[rank] : 0;
@@ -49,7 +49,7 @@ antq_flat_kernel(const T *__restrict__ x, T *__restrict__ out, int16_t *__restri
         s_thr[i] = cb->thr[i];
     }
     __syncthreads();
-    const bool fast = (cb->flags & ANTQ_CB_WELLSEP) != 0 && nlev >= 1;
+    const float fast = ((cb->flags & ANTQ_CB_WELLSEP) != 0 && nlev >= 1) ? cb->lim_idx : -1.0f;
     const float gmax = cb->gmax;
     const int K = cb->n_entries;
 
@@ -181,7 +181,7 @@ antq_mse_sweep_kernel(const T *__restrict__ x, const float *__restrict__ base_al
         s_thr[i] = cb->thr[i];
     }
     __syncthreads();
-    const bool fast = (cb->flags & ANTQ_CB_WELLSEP) != 0 && nlev >= 1;
+    const float fast = ((cb->flags & ANTQ_CB_WELLSEP) != 0 && nlev >= 1) ? cb->lim_idx : -1.0f;
     const float gmax = cb->gmax;
     const long long row = blockIdx.x / chunks_per_row;
     const int chunk = blockIdx.x % chunks_per_row;

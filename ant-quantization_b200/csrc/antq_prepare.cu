@@ -92,13 +92,16 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
     if (i == 0) {
         const float vmax = L > 0 ? lev[L - 1] : 0.0f, vmin = L > 0 ? lev[0] : 0.0f;
         int flags = 0;
-        // beyond the ends the winner is the extreme level as long as the runner-up cannot tie:
-        // gaps at both ends must exceed the fp32 resolution at the largest window we use.
-        bool sep = !s_flags_bad_sep && L >= 1 && fabsf(vmax) <= 4096.0f && fabsf(vmin) <= 4096.0f;
+        // Beyond the ends the winner is the extreme level unless the runner-up has a LATER scan index
+        // and their rounded distances coincide, which needs gap < ulp(distance): bound the window so
+        // that cannot happen (e.g. unsigned pot: 0 and 10*2^-14 tie for d < -10240 in the reference).
+        float lim_idx = 65536.0f;
         if (L >= 2) {
-            if (!((lev[L - 1] - lev[L - 2]) > 0.02f) && lcode[L - 2] > lcode[L - 1]) sep = false;
-            if (!((lev[1] - lev[0]) > 0.02f) && lcode[1] > lcode[0]) sep = false;
+            if (lcode[L - 2] > lcode[L - 1]) lim_idx = fminf(lim_idx, (lev[L - 1] - lev[L - 2]) * 2097152.0f);
+            if (lcode[1] > lcode[0]) lim_idx = fminf(lim_idx, (lev[1] - lev[0]) * 2097152.0f);
         }
+        bool sep = !s_flags_bad_sep && L >= 1 && fabsf(vmax) <= 4096.0f && fabsf(vmin) <= 4096.0f &&
+                   lim_idx >= fmaxf(fabsf(vmax), fabsf(vmin));
         if (sep) flags |= ANTQ_CB_WELLSEP;
         bool ste = !s_flags_bad_ste && vmax > 0.0f && vmin <= 0.0f;
         if (ste) flags |= ANTQ_CB_STE_EXACT;
@@ -141,7 +144,8 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
         float lim_pos = 2.0f * vmax;
         float lim_neg = vmin < 0.0f ? -2.0f * vmin : lim_pos;
         float lim = lim_pos < lim_neg ? lim_pos : lim_neg;
-        cb->lim = lim < 65536.0f ? lim : 65536.0f;
+        cb->lim = lim < lim_idx ? lim : lim_idx;
+        cb->lim_idx = lim_idx;
         cb->magic = ANTQ_CB_MAGIC;
     }
     if (i < ANTQ_MAX_GRID) {

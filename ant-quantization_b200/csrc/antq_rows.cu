@@ -78,28 +78,35 @@ template <> struct Pack2<__nv_bfloat16> {
 };
 
 template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct RowTables16 {
-    uint32_t X[NT];       // thresholds, duplicated in both halves
+    uint32_t X[NT];       // thresholds for x >= 0 (or for every x when !SYM), duplicated in both halves
+    uint32_t Xn[NT];      // SYM: thresholds on |x| for x < 0 -- they differ from X only where an exact tie
+                          // is representable (ties go to the LATER grid entry: up for +, toward 0 for -)
     uint32_t O[NT + 1];   // outputs, duplicated
-    uint32_t xlim, xovp;
+    uint32_t xlim, xovp, xovpn;
 
     // one 32-bit register = two elements (low half = even flat index)
+    template <bool TIES>
     __device__ __forceinline__ uint32_t pair(uint32_t xb, bool &special, uint32_t &ranks, uint32_t &victims) const {
         typedef typename Pack2<T>::v2 v2;
         const v2 x2 = Pack2<T>::from_u32(xb);
         const v2 ab = __habs2(x2);
         const v2 a2 = SYM ? ab : x2;
         special |= (__hle2_mask(ab, Pack2<T>::from_u32(xlim)) != 0xffffffffu);   // NaN/Inf/out-of-window
+        uint32_t neg = 0;
+        if (SYM && TIES) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));          // 0xffff where x < 0
         uint32_t q = O[0], m0 = 0, rk = 0;
 #pragma unroll
         for (int i = 0; i < NT; i++) {
-            const uint32_t m = __hge2_mask(a2, Pack2<T>::from_u32(X[i]));
+            const uint32_t t = (SYM && TIES) ? ((neg & Xn[i]) | (~neg & X[i])) : X[i];
+            const uint32_t m = __hge2_mask(a2, Pack2<T>::from_u32(t));
             if (i == 0) m0 = m;
             q = (m & O[i + 1]) | (~m & q);
             if (CODES) rk += m & 0x00010001u;
         }
         if (SYM) q |= (xb & 0x80008000u) & m0;   // restore the sign unless the level is zero
         if (OVP) {
-            const uint32_t mo = __hge2_mask(a2, Pack2<T>::from_u32(xovp));   // element is an outlier
+            const uint32_t t = (SYM && TIES) ? ((neg & xovpn) | (~neg & xovp)) : xovp;
+            const uint32_t mo = __hge2_mask(a2, Pack2<T>::from_u32(t));      // element is an outlier
             const uint32_t sw = __byte_perm(mo, 0, 0x1032);                  // swap halves
             const uint32_t kill = sw & ~(mo & 0x0000ffffu);  // odd dies if even is outlier; even dies if only odd is
             q &= ~kill;
@@ -112,23 +119,25 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct RowTables16
 
 template <int NT, bool SYM, bool OVP, bool CODES> struct RowTables32 {
     float X[NT];
+    float Xn[NT];         // SYM: thresholds on |x| for negative x (fp32 x-space resolves ties, so they differ)
     float O[NT + 1];
-    float xlim, xovp;
+    float xlim, xovp, xovpn;
     __device__ __forceinline__ float one(float x, bool &special, int &rank, bool &outlier) const {
         const float a = SYM ? fabsf(x) : x;
+        const bool neg = SYM && (__float_as_int(x) < 0);
         special |= !(fabsf(x) <= xlim);
         float q = O[0];
         bool m0 = false;
         int rk = 0;
 #pragma unroll
         for (int i = 0; i < NT; i++) {
-            const bool m = a >= X[i];
+            const bool m = a >= (neg ? Xn[i] : X[i]);
             if (i == 0) m0 = m;
             q = m ? O[i + 1] : q;
             if (CODES) rk += m ? 1 : 0;
         }
         if (SYM && m0) q = __uint_as_float(__float_as_uint(q) | (__float_as_uint(x) & 0x80000000u));
-        if (OVP) outlier = a >= xovp;
+        if (OVP) outlier = a >= (neg ? xovpn : xovp);
         rank = rk;
         return q;
     }
@@ -177,18 +186,24 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct SegmentWork
     static constexpr int VEC = 8;
     RowTables16<T, NT, SYM, OVP, CODES> tab;
 
-    __device__ __forceinline__ void load(const T *sX, const T *sO, const AntqCodebook *__restrict__ cb, float s) {
+    __device__ __forceinline__ void load(const T *sX, const T *sXn, const T *sO, const AntqCodebook *__restrict__ cb,
+                                         float s) {
 #pragma unroll
         for (int i = 0; i < NT; i++) tab.X[i] = Pack2<T>::dup(sX[i]);
+#pragma unroll
+        for (int i = 0; i < NT; i++) tab.Xn[i] = Pack2<T>::dup(sXn[i]);
 #pragma unroll
         for (int i = 0; i <= NT; i++) tab.O[i] = Pack2<T>::dup(sO[i]);
         const float xl = __fmul_rn(__fmul_rn(cb->lim, s), 0.9990234375f);   // conservative window in x-space
         tab.xlim = Pack2<T>::dup(A::from_f32_rz(xl));
         const int oi = cb->ovp_index;
-        tab.xovp = Pack2<T>::dup((OVP && oi >= 0 && oi < NT) ? sX[oi] : A::from_bits(A::kInf));
+        const bool has = OVP && oi >= 0 && oi < NT;
+        tab.xovp = Pack2<T>::dup(has ? sX[oi] : A::from_bits(A::kInf));
+        tab.xovpn = Pack2<T>::dup(has ? sXn[oi] : A::from_bits(A::kInf));
     }
 
     // returns true if this lane skipped at least one vector (NaN/Inf/outside the exact window)
+    template <bool TIES>
     __device__ __forceinline__ bool run(const AntqCodebook *__restrict__ cb, const T *xrow, T *orow,
                                         int16_t *crow, int nvec, int lane) const {
         const uint4 *xin = reinterpret_cast<const uint4 *>(xrow);
@@ -209,10 +224,10 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct SegmentWork
                     bool special = false;
                     uint32_t rk[4], vi[4] = {0, 0, 0, 0};
                     uint4 q;
-                    q.x = tab.pair(r[j].x, special, rk[0], vi[0]);
-                    q.y = tab.pair(r[j].y, special, rk[1], vi[1]);
-                    q.z = tab.pair(r[j].z, special, rk[2], vi[2]);
-                    q.w = tab.pair(r[j].w, special, rk[3], vi[3]);
+                    q.x = tab.template pair<TIES>(r[j].x, special, rk[0], vi[0]);
+                    q.y = tab.template pair<TIES>(r[j].y, special, rk[1], vi[1]);
+                    q.z = tab.template pair<TIES>(r[j].z, special, rk[2], vi[2]);
+                    q.w = tab.template pair<TIES>(r[j].w, special, rk[3], vi[3]);
                     any_special |= special;
                     if (!special) {      // special vectors are left untouched for antq_fixup_pass
                         antq_stg_stream(oout + v, q);
@@ -244,17 +259,23 @@ template <int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker<float, NT
     static constexpr int VEC = 4;
     RowTables32<NT, SYM, OVP, CODES> tab;
 
-    __device__ __forceinline__ void load(const T *sX, const T *sO, const AntqCodebook *__restrict__ cb, float s) {
+    __device__ __forceinline__ void load(const T *sX, const T *sXn, const T *sO, const AntqCodebook *__restrict__ cb,
+                                         float s) {
 #pragma unroll
         for (int i = 0; i < NT; i++) tab.X[i] = sX[i];
+#pragma unroll
+        for (int i = 0; i < NT; i++) tab.Xn[i] = sXn[i];
 #pragma unroll
         for (int i = 0; i <= NT; i++) tab.O[i] = sO[i];
         tab.xlim = __fmul_rn(__fmul_rn(cb->lim, s), 0.9990234375f);
         const int oi = cb->ovp_index;
-        tab.xovp = (OVP && oi >= 0 && oi < NT) ? sX[oi] : __int_as_float(0x7f800000);
+        const bool has = OVP && oi >= 0 && oi < NT;
+        tab.xovp = has ? sX[oi] : __int_as_float(0x7f800000);
+        tab.xovpn = has ? sXn[oi] : __int_as_float(0x7f800000);
     }
 
     // returns true if this lane skipped at least one vector (NaN/Inf/outside the exact window)
+    template <bool TIES>      // fp32 x-space always resolves ties: the flag is ignored
     __device__ __forceinline__ bool run(const AntqCodebook *__restrict__ cb, const T *xrow, T *orow,
                                         int16_t *crow, int nvec, int lane) const {
         const uint4 *xin = reinterpret_cast<const uint4 *>(xrow);
@@ -313,10 +334,11 @@ template <int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker<float, NT
 };
 
 template <typename T, int NT, bool SYM, bool OVP, bool CODES>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 8 : (NT <= 15 ? 6 : 3))) antq_rows_kernel(const RowsParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 6 : (NT <= 15 ? 4 : 2))) antq_rows_kernel(const RowsParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
     __shared__ __align__(16) T sX[kWarpsPerCta][32];
+    __shared__ __align__(16) T sXn[kWarpsPerCta][32];
     __shared__ __align__(16) T sO[kWarpsPerCta][32];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 8 : (NT <= 15 ? 
     SegmentWorker<T, NT, SYM, OVP, CODES> worker;
     long long cur_row = -1;
     float s = 0.0f;
-    bool row_fast = false;
+    bool row_ok = false, row_ties = false;
 
     const long long sg0 = w * p.segs_per_warp;
     const long long sg1 = (sg0 + p.segs_per_warp) < p.total_segs ? (sg0 + p.segs_per_warp) : p.total_segs;
@@ -342,19 +364,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 8 : (NT <= 15 ? 
             const float alpha = __ldg(p.alpha + (p.alpha_per_row ? row : 0));
             s = __fdiv_rn(alpha, gmax);                          // scale = alpha / max(grid)
             const bool s_ok = s > 0.0f && s < __int_as_float(0x7f800000);
-            T Xl = A::from_bits(A::kInf), Ol = A::from_bits(0);
-            bool tie_free = true;
+            T Xl = A::from_bits(A::kInf), Xnl = A::from_bits(A::kInf), Ol = A::from_bits(0);
             if (s_ok) {
                 if (lane < nt_real) {
                     bool near;
                     if (SYM) {
                         Xl = antq_x_threshold<T>(cb->mag_tpos[lane], s, &near);
-                        if (near) {   // a positive and a negative input could land on different sides of a tie
-                            const T xn = antq_x_threshold_exact<T>(cb->mag_tneg[lane], s);
-                            tie_free = A::bits(Xl) == A::bits(xn);
-                        }
+                        // unless the shortcut proved both sides equal, a negative input can land on the
+                        // other side of a representable tie: give it its own threshold
+                        Xnl = near ? antq_x_threshold_exact<T>(cb->mag_tneg[lane], s) : Xl;
                     } else {
                         Xl = antq_x_threshold<T>(cb->thr[lane], s, &near);
+                        Xnl = Xl;
                     }
                 }
                 if (lane <= nt_real) {
@@ -362,12 +383,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 8 : (NT <= 15 ? 
                     Ol = A::from_f32_rn(__fmul_rn(lv, s));
                 }
             }
-            row_fast = __all_sync(0xffffffffu, s_ok && tie_free);
+            row_ok = s_ok;
+            row_ties = __any_sync(0xffffffffu, A::bits(Xl) != A::bits(Xnl));
             __syncwarp();
             sX[wib][lane] = Xl;
+            sXn[wib][lane] = Xnl;
             sO[wib][lane] = Ol;
             __syncwarp();
-            worker.load(sX[wib], sO[wib], cb, s);
+            worker.load(sX[wib], sXn[wib], sO[wib], cb, s);
         }
 
         const long long col0 = (long long)seg * p.seg_len;
@@ -379,8 +402,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 8 : (NT <= 15 ? 
         T *orow = reinterpret_cast<T *>(p.out) + base;
         int16_t *crow = CODES ? p.codes + base : nullptr;
 
-        if (row_fast) {
-            const bool skipped = worker.run(cb, xrow, orow, crow, nvec, lane);
+        if (row_ok) {
+            const bool skipped = row_ties ? worker.template run<true>(cb, xrow, orow, crow, nvec, lane)
+                                          : worker.template run<false>(cb, xrow, orow, crow, nvec, lane);
             if (__any_sync(0xffffffffu, skipped))
                 antq_fixup_pass<T, OVP>(cb, s, worker.xlim_f32(), xrow, orow, crow, nvec, lane);
         } else {
