@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libantq.so")
-SOURCES = ["antq_prepare.cu", "antq_rows.cu", "antq_flat.cu", "antq_capi.cu"]
+SOURCES = ["antq_prepare.cu", "antq_rows.cu", "antq_flat.cu", "antq_capi.cu", "antq_debug.cu"]
 HEADERS = ["antq_common.cuh", os.path.join("..", "..", "include", "antq.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

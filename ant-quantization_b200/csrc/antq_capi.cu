@@ -7,7 +7,8 @@
 #include "antq_common.cuh"
 
 int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
-                     long long cols, int dtype, const AntqCodebook *cb, int nt, bool sym, bool ovp, cudaStream_t st);
+                     long long cols, int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp,
+                     cudaStream_t st);
 int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
 int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
@@ -92,9 +93,7 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
     if (plan < 0) return plan;
     const AntqCodebook *cb = (const AntqCodebook *)codebook;
     if (plan == 1) {
-        const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
-        const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
-        return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, nt, sym, ovp,
+        return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
                                 (cudaStream_t)stream);
     }
     return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp,

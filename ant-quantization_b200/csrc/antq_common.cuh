@@ -207,6 +207,43 @@ __device__ __forceinline__ void antq_stg_stream(uint4 *p, const uint4 &v) {
                  : "memory");
 }
 
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier ---------------------
+// cp.async.bulk moves a contiguous, 16-byte aligned span without occupying registers or
+// LSU issue slots while it is in flight; SASS: UBLKCP + SYNCS.
+__device__ __forceinline__ uint32_t antq_smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void antq_mbar_init(uint64_t *bar, unsigned count) {
+    // NOTE: no fence.mbarrier_init.release.cluster here -- ptxas lowers any cluster-scope fence to
+    // CCTL.IVALL (an SM-wide L1 invalidate), which serialised every CTA start (profiles/r01_notes.md).
+    // The barrier is CTA-local: fence.proxy.async (issued by the same lane before the copy) + __syncwarp suffice.
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(antq_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void antq_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void antq_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(antq_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     antq_smem_u32(dst_smem)),
+                 "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(antq_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void antq_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ANTQ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ANTQ_DONE;\n"
+        "bra ANTQ_WAIT;\n"
+        "ANTQ_DONE:\n"
+        "}\n" ::"r"(antq_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // Reference arithmetic for ONE element, literally:  d = x / s; q = scan(d).
 struct AntqExact {
     float d, q;

@@ -4,26 +4,42 @@
 // scan kernel it calls (A/quant/quant_kernel.cu:11-39): ~9 launches and 7 reads +
 // 7 writes of the tensor become ONE launch, one read, one write.
 //
-// Idea (proved bit-exact on exhaustive fp16 inputs in tests/test_xspace_model.py):
+// Arithmetic (proved bit-exact on exhaustive fp16 inputs in tests/test_xspace_model.py):
 // the reference computes d = fl32(x / s), picks the grid level by a scan, and
 // returns fl32(((q - d) + d) * s).  fl32(x / s) is monotone in x, so every
 // d-space threshold of the prepared codebook maps to an exact x-space threshold
 //      X_r = min{ x in dtype : fl32(x / s) >= thr_r }
 // and inside the window |d| <= lim the STE sum is exact, so the result is simply
-// O_j = RN_dtype(fl32(level_j * s)).  One warp owns one row segment: its lanes
-// build the row's (X_r, O_j) tables in parallel (lane r <-> threshold r), share
-// them through shared memory, and then stream the segment with 128-bit loads:
-// per 32-bit register (two fp16 values) the work is one packed compare + one
-// LOP3 per threshold -- no division, no table lookup, no divergent branch.
-// Values outside the window, NaN/Inf, rows whose scale is not a positive finite
-// number, and rows where a positive/negative tie would differ take the literal
-// reference arithmetic (antq_slow_vec) -- rare, and exact by construction.
+// O_j = RN_dtype(fl32(level_j * s)).  Per 32-bit register (two fp16 values) the work
+// is one packed compare (HSET2) + one LOP3 per threshold -- no division, no lookup.
+// Values outside the window, NaN/Inf and rows whose scale is not a positive finite
+// number take the literal reference arithmetic (antq_slow_vec): rare, exact.
+//
+// Execution shape (B200): a PERSISTENT grid of 148 x 4 CTAs x 4 warps.  The tensor
+// is cut into 2 KiB chunks that never straddle a row; every warp owns an equal,
+// contiguous range of chunks (static balance, no tail wave) and walks it with a
+// 4-deep ring of TMA bulk copies (cp.async.bulk -> shared memory, completion on an
+// mbarrier), so up to 6 KiB per warp / 96 KiB per SM are in flight without holding
+// registers.  When the row changes the warp rebuilds its (X, O) tables: lane r owns
+// threshold r, its codebook values stay in registers for the whole kernel and the
+// next row's alpha is prefetched, so the rebuild is ~60 instructions off the
+// critical path of the copies already in flight.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "antq_common.cuh"
 
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kUnroll = 4;
+constexpr int kCtasPerSm = 3;
+constexpr int kNumSms = 148;
+constexpr int kRing = 8;                 // chunks in flight + in use per warp
+constexpr int kChunkBytes = 2048;        // one chunk = 128 vectors = 4 per lane
+constexpr int kChunkVecs = kChunkBytes / 16;
+constexpr int kVecPerLane = kChunkVecs / 32;
+constexpr int kTableWords = 32;          // per table, per warp (uint32 / float)
+constexpr int kWarpSmemBytes = kRing * kChunkBytes + 3 * kTableWords * 4 + 128;   // ring | X | Xn | O | mbarriers
 
 template <typename T, bool OVP>
 __device__ __noinline__ void antq_slow_vec(const AntqCodebook *__restrict__ cb, float s, const T *xg, T *og,
@@ -58,33 +74,100 @@ __device__ __noinline__ void antq_slow_vec(const AntqCodebook *__restrict__ cb, 
     }
 }
 
+// Cold pass over a chunk in which some vector was skipped by the fast path: the same window
+// predicate is re-evaluated in fp32 and exactly the skipped vectors get the reference arithmetic.
+// (The fast path stores nothing for them, so this also works in place.)  `all` = row scale invalid.
+template <typename T, bool OVP>
+__device__ __noinline__ void antq_fixup_chunk(const AntqCodebook *__restrict__ cb, float s, float xlim, bool all,
+                                              const T *xg, T *og, int16_t *cg, int nvec, int lane) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    for (int v = lane; v < nvec; v += 32) {
+        const T *xv = xg + (long long)v * VEC;
+        bool special = all;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) special |= !(fabsf(A::to_f32(xv[e])) <= xlim);
+        if (special)
+            antq_slow_vec<T, OVP>(cb, s, xv, og + (long long)v * VEC, cg ? cg + (long long)v * VEC : nullptr, VEC);
+    }
+}
+
+template <bool SYM>
+__device__ __forceinline__ int16_t antq_rank_to_code(const AntqCodebook *__restrict__ cb, int mid, int rank, bool neg) {
+    int lvl = SYM ? (mid + (neg ? -rank : rank)) : rank;
+    return (int16_t)cb->level_code[lvl];
+}
+
 // ---- packed 16-bit (fp16 / bf16) chain --------------------------------------
-template <typename T> struct Pack2;
+template <typename T> struct Pack2 {
+    typedef float2 v2;     // unused for fp32
+    __device__ static __forceinline__ v2 from_u32(uint32_t) { return make_float2(0.f, 0.f); }
+};
 template <> struct Pack2<__half> {
     typedef __half2 v2;
     __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
-    __device__ static __forceinline__ uint32_t dup(__half h) {
-        uint32_t b = __half_as_ushort(h);
-        return b | (b << 16);
-    }
 };
 template <> struct Pack2<__nv_bfloat16> {
     typedef __nv_bfloat162 v2;
     __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
-    __device__ static __forceinline__ uint32_t dup(__nv_bfloat16 h) {
-        uint32_t b = __bfloat16_as_ushort(h);
-        return b | (b << 16);
-    }
 };
 
-template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct RowTables16 {
-    uint32_t X[NT];       // thresholds for x >= 0 (or for every x when !SYM), duplicated in both halves
-    uint32_t Xn[NT];      // SYM: thresholds on |x| for x < 0 -- they differ from X only where an exact tie
-                          // is representable (ties go to the LATER grid entry: up for +, toward 0 for -)
-    uint32_t O[NT + 1];   // outputs, duplicated
+// Word a lane publishes for its table entry: 16-bit types are duplicated into both halves.
+template <typename T> __device__ __forceinline__ uint32_t antq_table_word(T v) {
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t b = AntqType<T>::bits(v);
+        return b | (b << 16);
+    } else {
+        return __float_as_uint(v);
+    }
+}
+
+template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct Tables {
+    static constexpr bool IS16 = sizeof(T) == 2;
+    uint32_t X[NT];       // thresholds for x >= 0 (or every x when !SYM)
+    uint32_t Xn[NT];      // SYM: thresholds on |x| for x < 0 -- differ from X only where a tie is representable
+                          // (ties go to the LATER grid entry: up for positive d, toward zero for negative d)
+    uint32_t O[NT + 1];   // dequantised outputs per level / magnitude
     uint32_t xlim, xovp, xovpn;
 
-    // one 32-bit register = two elements (low half = even flat index)
+    __device__ __forceinline__ void load(const uint32_t *sX, const uint32_t *sXn, const uint32_t *sO, float lim, int oi,
+                                         float s) {
+        // vectorised smem reads: 32-word tables, 16-byte aligned
+        constexpr int NX = (NT + 3) / 4, NO = (NT + 4) / 4;
+        uint4 bx[NX], bn[NX], bo[NO];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+            bx[i] = reinterpret_cast<const uint4 *>(sX)[i];
+            bn[i] = reinterpret_cast<const uint4 *>(sXn)[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NO; i++) bo[i] = reinterpret_cast<const uint4 *>(sO)[i];
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            const uint4 a = bx[i / 4], b = bn[i / 4];
+            X[i] = (i % 4 == 0) ? a.x : (i % 4 == 1) ? a.y : (i % 4 == 2) ? a.z : a.w;
+            Xn[i] = (i % 4 == 0) ? b.x : (i % 4 == 1) ? b.y : (i % 4 == 2) ? b.z : b.w;
+        }
+#pragma unroll
+        for (int i = 0; i <= NT; i++) {
+            const uint4 a = bo[i / 4];
+            O[i] = (i % 4 == 0) ? a.x : (i % 4 == 1) ? a.y : (i % 4 == 2) ? a.z : a.w;
+        }
+        const float xl = __fmul_rn(__fmul_rn(lim, s), 0.9990234375f);   // conservative window in x-space
+        xlim = antq_table_word<T>(AntqType<T>::from_f32_rz(xl));
+        const bool has = OVP && oi >= 0 && oi < NT;
+        const uint32_t inf = antq_table_word<T>(AntqType<T>::from_bits(AntqType<T>::kInf));
+        xovp = has ? sX[oi] : inf;
+        xovpn = has ? sXn[oi] : inf;
+    }
+    __device__ __forceinline__ float xlim_f32() const {
+        if constexpr (IS16)
+            return AntqType<T>::to_f32(AntqType<T>::from_bits((typename AntqType<T>::bits_t)(xlim & 0xffffu)));
+        else
+            return __uint_as_float(xlim);
+    }
+
+    // 16-bit: one 32-bit register = two elements (low half = even flat index)
     template <bool TIES>
     __device__ __forceinline__ uint32_t pair(uint32_t xb, bool &special, uint32_t &ranks, uint32_t &victims) const {
         typedef typename Pack2<T>::v2 v2;
@@ -115,192 +198,84 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct RowTables16
         ranks = rk;
         return q;
     }
-};
 
-template <int NT, bool SYM, bool OVP, bool CODES> struct RowTables32 {
-    float X[NT];
-    float Xn[NT];         // SYM: thresholds on |x| for negative x (fp32 x-space resolves ties, so they differ)
-    float O[NT + 1];
-    float xlim, xovp, xovpn;
+    // fp32: one element per register; fp32 x-space resolves ties, so negatives always use Xn
     __device__ __forceinline__ float one(float x, bool &special, int &rank, bool &outlier) const {
         const float a = SYM ? fabsf(x) : x;
         const bool neg = SYM && (__float_as_int(x) < 0);
-        special |= !(fabsf(x) <= xlim);
-        float q = O[0];
+        special |= !(fabsf(x) <= __uint_as_float(xlim));
+        float q = __uint_as_float(O[0]);
         bool m0 = false;
         int rk = 0;
 #pragma unroll
         for (int i = 0; i < NT; i++) {
-            const bool m = a >= (neg ? Xn[i] : X[i]);
+            const bool m = a >= __uint_as_float(neg ? Xn[i] : X[i]);
             if (i == 0) m0 = m;
-            q = m ? O[i + 1] : q;
+            q = m ? __uint_as_float(O[i + 1]) : q;
             if (CODES) rk += m ? 1 : 0;
         }
         if (SYM && m0) q = __uint_as_float(__float_as_uint(q) | (__float_as_uint(x) & 0x80000000u));
-        if (OVP) outlier = a >= (neg ? xovpn : xovp);
+        if (OVP) outlier = a >= __uint_as_float(neg ? xovpn : xovp);
         rank = rk;
         return q;
     }
-};
 
-// Cold second pass over a segment in which some vector was skipped by the fast loop: the same
-// window predicate is re-evaluated in fp32, and exactly the skipped vectors get the literal
-// reference arithmetic.  (The fast loop stores nothing for them, so this also works in place.)
-template <typename T, bool OVP>
-__device__ __noinline__ void antq_fixup_pass(const AntqCodebook *__restrict__ cb, float s, float xlim, const T *xrow,
-                                             T *orow, int16_t *crow, int nvec, int lane) {
-    typedef AntqType<T> A;
-    constexpr int VEC = A::kVec;
-    for (int v = lane; v < nvec; v += 32) {
-        const T *xv = xrow + (long long)v * VEC;
-        bool special = false;
-#pragma unroll
-        for (int e = 0; e < VEC; e++) special |= !(fabsf(A::to_f32(xv[e])) <= xlim);
-        if (special)
-            antq_slow_vec<T, OVP>(cb, s, xv, orow + (long long)v * VEC, crow ? crow + (long long)v * VEC : nullptr,
-                                  VEC);
-    }
-}
-
-struct RowsParams {
-    const void *x;
-    void *out;
-    int16_t *codes;
-    const float *alpha;
-    const AntqCodebook *cb;
-    long long rows, cols, total_segs, total_warps;
-    int alpha_per_row, segs_per_row, seg_len, segs_per_warp;
-};
-
-template <bool SYM>
-__device__ __forceinline__ int16_t antq_rank_to_code(const AntqCodebook *__restrict__ cb, int rank, bool neg) {
-    int lvl = SYM ? (cb->mid + (neg ? -rank : rank)) : rank;
-    return (int16_t)cb->level_code[lvl];
-}
-
-// Per-row tables in registers + the streaming loop over one segment.
-template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker;
-
-template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker {   // 16-bit element types
-    typedef AntqType<T> A;
-    static constexpr int VEC = 8;
-    RowTables16<T, NT, SYM, OVP, CODES> tab;
-
-    __device__ __forceinline__ void load(const T *sX, const T *sXn, const T *sO, const AntqCodebook *__restrict__ cb,
-                                         float s) {
-#pragma unroll
-        for (int i = 0; i < NT; i++) tab.X[i] = Pack2<T>::dup(sX[i]);
-#pragma unroll
-        for (int i = 0; i < NT; i++) tab.Xn[i] = Pack2<T>::dup(sXn[i]);
-#pragma unroll
-        for (int i = 0; i <= NT; i++) tab.O[i] = Pack2<T>::dup(sO[i]);
-        const float xl = __fmul_rn(__fmul_rn(cb->lim, s), 0.9990234375f);   // conservative window in x-space
-        tab.xlim = Pack2<T>::dup(A::from_f32_rz(xl));
-        const int oi = cb->ovp_index;
-        const bool has = OVP && oi >= 0 && oi < NT;
-        tab.xovp = Pack2<T>::dup(has ? sX[oi] : A::from_bits(A::kInf));
-        tab.xovpn = Pack2<T>::dup(has ? sXn[oi] : A::from_bits(A::kInf));
-    }
-
-    // returns true if this lane skipped at least one vector (NaN/Inf/outside the exact window)
+    // One chunk (<= 4 vectors per lane) from shared memory to global.  Returns true if this lane
+    // skipped a vector (left for antq_fixup_chunk).
     template <bool TIES>
-    __device__ __forceinline__ bool run(const AntqCodebook *__restrict__ cb, const T *xrow, T *orow,
-                                        int16_t *crow, int nvec, int lane) const {
-        const uint4 *xin = reinterpret_cast<const uint4 *>(xrow);
-        uint4 *oout = reinterpret_cast<uint4 *>(orow);
-        const int K = cb->n_entries;
+    __device__ __forceinline__ bool chunk(const AntqCodebook *__restrict__ cb, const uint4 *sv, T *og, int16_t *cg,
+                                          int nvec, int lane, int mid, int K, int dbg) const {
+        constexpr int VEC = AntqType<T>::kVec;
+        uint4 *oout = reinterpret_cast<uint4 *>(og);
         bool any_special = false;
-        for (int v0 = 0; v0 < nvec; v0 += 32 * kUnroll) {
-            uint4 r[kUnroll];
+        uint4 r[kVecPerLane];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) {
-                const int v = v0 + j * 32 + lane;
-                if (v < nvec) r[j] = antq_ldg_stream(xin + v);
-            }
+        for (int j = 0; j < kVecPerLane; j++) {
+            const int v = j * 32 + lane;
+            if (v < nvec) r[j] = sv[v];                       // LDS.128, conflict free
+        }
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) {
-                const int v = v0 + j * 32 + lane;
-                if (v < nvec) {
-                    bool special = false;
-                    uint32_t rk[4], vi[4] = {0, 0, 0, 0};
-                    uint4 q;
-                    q.x = tab.template pair<TIES>(r[j].x, special, rk[0], vi[0]);
-                    q.y = tab.template pair<TIES>(r[j].y, special, rk[1], vi[1]);
-                    q.z = tab.template pair<TIES>(r[j].z, special, rk[2], vi[2]);
-                    q.w = tab.template pair<TIES>(r[j].w, special, rk[3], vi[3]);
+        for (int j = 0; j < kVecPerLane; j++) {
+            const int v = j * 32 + lane;
+            if (v < nvec) {
+                bool special = false;
+                uint4 q;
+                if constexpr (IS16) {
+                    uint32_t rk[4] = {0, 0, 0, 0}, vi[4] = {0, 0, 0, 0};
+                    if (dbg & 2) {
+                        q = r[j];
+                    } else {
+                        q.x = pair<TIES>(r[j].x, special, rk[0], vi[0]);
+                        q.y = pair<TIES>(r[j].y, special, rk[1], vi[1]);
+                        q.z = pair<TIES>(r[j].z, special, rk[2], vi[2]);
+                        q.w = pair<TIES>(r[j].w, special, rk[3], vi[3]);
+                    }
                     any_special |= special;
-                    if (!special) {      // special vectors are left untouched for antq_fixup_pass
+                    if ((dbg & 1) && q.x != 0x12345678u) continue;
+                    if (!special) {
                         antq_stg_stream(oout + v, q);
                         if (CODES) {
                             const uint32_t xb[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
                             __align__(16) int16_t cc[8];
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
-                                cc[2 * k] = antq_rank_to_code<SYM>(cb, rk[k] & 0xffff, (xb[k] & 0x8000u) != 0);
-                                cc[2 * k + 1] = antq_rank_to_code<SYM>(cb, rk[k] >> 16, (xb[k] & 0x80000000u) != 0);
+                                cc[2 * k] = antq_rank_to_code<SYM>(cb, mid, rk[k] & 0xffff, (xb[k] & 0x8000u) != 0);
+                                cc[2 * k + 1] =
+                                    antq_rank_to_code<SYM>(cb, mid, rk[k] >> 16, (xb[k] & 0x80000000u) != 0);
                                 if (OVP && (vi[k] & 0xffffu)) cc[2 * k] = (int16_t)K;
                                 if (OVP && (vi[k] >> 16)) cc[2 * k + 1] = (int16_t)K;
                             }
-                            *reinterpret_cast<uint4 *>(crow + (long long)v * VEC) = *reinterpret_cast<uint4 *>(cc);
+                            *reinterpret_cast<uint4 *>(cg + (long long)v * VEC) = *reinterpret_cast<uint4 *>(cc);
                         }
                     }
-                }
-            }
-        }
-        return any_special;
-    }
-    __device__ __forceinline__ float xlim_f32() const {
-        return A::to_f32(A::from_bits((typename A::bits_t)(tab.xlim & 0xffffu)));
-    }
-};
-
-template <int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker<float, NT, SYM, OVP, CODES> {
-    typedef float T;
-    static constexpr int VEC = 4;
-    RowTables32<NT, SYM, OVP, CODES> tab;
-
-    __device__ __forceinline__ void load(const T *sX, const T *sXn, const T *sO, const AntqCodebook *__restrict__ cb,
-                                         float s) {
-#pragma unroll
-        for (int i = 0; i < NT; i++) tab.X[i] = sX[i];
-#pragma unroll
-        for (int i = 0; i < NT; i++) tab.Xn[i] = sXn[i];
-#pragma unroll
-        for (int i = 0; i <= NT; i++) tab.O[i] = sO[i];
-        tab.xlim = __fmul_rn(__fmul_rn(cb->lim, s), 0.9990234375f);
-        const int oi = cb->ovp_index;
-        const bool has = OVP && oi >= 0 && oi < NT;
-        tab.xovp = has ? sX[oi] : __int_as_float(0x7f800000);
-        tab.xovpn = has ? sXn[oi] : __int_as_float(0x7f800000);
-    }
-
-    // returns true if this lane skipped at least one vector (NaN/Inf/outside the exact window)
-    template <bool TIES>      // fp32 x-space always resolves ties: the flag is ignored
-    __device__ __forceinline__ bool run(const AntqCodebook *__restrict__ cb, const T *xrow, T *orow,
-                                        int16_t *crow, int nvec, int lane) const {
-        const uint4 *xin = reinterpret_cast<const uint4 *>(xrow);
-        uint4 *oout = reinterpret_cast<uint4 *>(orow);
-        const int K = cb->n_entries;
-        bool any_special = false;
-        for (int v0 = 0; v0 < nvec; v0 += 32 * kUnroll) {
-            uint4 r[kUnroll];
-#pragma unroll
-            for (int j = 0; j < kUnroll; j++) {
-                const int v = v0 + j * 32 + lane;
-                if (v < nvec) r[j] = antq_ldg_stream(xin + v);
-            }
-#pragma unroll
-            for (int j = 0; j < kUnroll; j++) {
-                const int v = v0 + j * 32 + lane;
-                if (v < nvec) {
-                    bool special = false;
+                } else {
                     const float xv[4] = {__uint_as_float(r[j].x), __uint_as_float(r[j].y), __uint_as_float(r[j].z),
                                          __uint_as_float(r[j].w)};
                     float qv[4];
                     int rk[4];
                     bool ol[4] = {false, false, false, false}, vict[4] = {false, false, false, false};
 #pragma unroll
-                    for (int k = 0; k < 4; k++) qv[k] = tab.one(xv[k], special, rk[k], ol[k]);
+                    for (int k = 0; k < 4; k++) qv[k] = one(xv[k], special, rk[k], ol[k]);
                     if (OVP) {
 #pragma unroll
                         for (int k = 0; k < 4; k += 2) {
@@ -312,17 +287,17 @@ template <int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker<float, NT
                     }
                     any_special |= special;
                     if (!special) {
-                        uint4 q = {__float_as_uint(qv[0]), __float_as_uint(qv[1]), __float_as_uint(qv[2]),
-                                   __float_as_uint(qv[3])};
+                        q = make_uint4(__float_as_uint(qv[0]), __float_as_uint(qv[1]), __float_as_uint(qv[2]),
+                                       __float_as_uint(qv[3]));
                         antq_stg_stream(oout + v, q);
                         if (CODES) {
                             __align__(8) int16_t cc[4];
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
-                                cc[k] = antq_rank_to_code<SYM>(cb, rk[k], (__float_as_uint(xv[k]) >> 31) != 0);
+                                cc[k] = antq_rank_to_code<SYM>(cb, mid, rk[k], (__float_as_uint(xv[k]) >> 31) != 0);
                                 if (OVP && vict[k]) cc[k] = (int16_t)K;
                             }
-                            *reinterpret_cast<uint2 *>(crow + (long long)v * VEC) = *reinterpret_cast<uint2 *>(cc);
+                            *reinterpret_cast<uint2 *>(cg + (long long)v * VEC) = *reinterpret_cast<uint2 *>(cc);
                         }
                     }
                 }
@@ -330,104 +305,199 @@ template <int NT, bool SYM, bool OVP, bool CODES> struct SegmentWorker<float, NT
         }
         return any_special;
     }
-    __device__ __forceinline__ float xlim_f32() const { return tab.xlim; }
 };
 
+struct RowsParams {
+    const void *x;
+    void *out;
+    int16_t *codes;
+    const float *alpha;
+    const AntqCodebook *cb;
+    long long rows, cols, total_chunks;
+    int alpha_per_row, chunks_per_row, chunk_elems, total_warps;
+    int nt_real, mid, ovp_index, n_entries;            // codebook header, from the host-side antq_codebook_info
+    float gmax, lim;
+    int debug;          // ANTQ_DEBUG experiments: 1 = no stores, 2 = no chain (copy), 4 = no table rebuild
+};
+
+// Exact (X, Xn) for a 16-bit type when the division-free shortcut could not prove them
+// (p = t*s within 16 fp32-ulps of a representable value): at most three divisions.
+template <typename T>
+__device__ __noinline__ void antq_x_threshold16_near(float tpos, float tneg, float s, T *xp, T *xn) {
+    typedef AntqType<T> A;
+    T c = A::from_f32_rn(__fmul_rn(tpos, s));
+    float qc = __fdiv_rn(A::to_f32(c), s);
+    if (qc >= tpos) {
+        const T p = antq_next_down(c);
+        const float qp = __fdiv_rn(A::to_f32(p), s);
+        if (!antq_is_inf(p) && qp >= tpos) { c = p; qc = qp; }
+    } else {
+        // RN(t*s) is within one step of the answer, but keep walking if it is not (never observed)
+#pragma unroll 1
+        for (int it = 0; it < 6 && !(qc >= tpos); ++it) {
+            c = antq_next_up(c);
+            qc = __fdiv_rn(A::to_f32(c), s);
+        }
+    }
+    *xp = c;
+    // the next 16-bit value is thousands of fp32-ulps further, tneg only a few: one test decides
+    *xn = (qc >= tneg) ? c : antq_next_up(c);
+}
+
 template <typename T, int NT, bool SYM, bool OVP, bool CODES>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? 6 : (NT <= 15 ? 4 : 2))) antq_rows_kernel(const RowsParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (NT <= 7 ? kCtasPerSm : (NT <= 15 ? 3 : 2)))
+antq_rows_kernel(const RowsParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
-    __shared__ __align__(16) T sX[kWarpsPerCta][32];
-    __shared__ __align__(16) T sXn[kWarpsPerCta][32];
-    __shared__ __align__(16) T sO[kWarpsPerCta][32];
-
+    extern __shared__ __align__(128) unsigned char antq_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long w = (long long)blockIdx.x * kWarpsPerCta + wib;
-    if (w >= p.total_warps) return;
-    const AntqCodebook *__restrict__ cb = p.cb;
-    const int nt_real = SYM ? cb->n_mag - 1 : cb->n_levels - 1;
-    const float gmax = cb->gmax;
+    unsigned char *wbase = antq_smem + (size_t)wib * kWarpSmemBytes;
+    uint32_t *sX = reinterpret_cast<uint32_t *>(wbase + kRing * kChunkBytes);
+    uint32_t *sXn = sX + kTableWords;
+    uint32_t *sO = sXn + kTableWords;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sO + kTableWords);
 
-    SegmentWorker<T, NT, SYM, OVP, CODES> worker;
+    const int w = blockIdx.x * kWarpsPerCta + wib;
+    // equal contiguous share of the chunk list
+    const long long c_begin = (p.total_chunks * w) / p.total_warps;
+    const long long c_end = (p.total_chunks * (w + 1)) / p.total_warps;
+    if (c_begin >= c_end) return;
+    const AntqCodebook *__restrict__ cb = p.cb;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kRing; k++) antq_mbar_init(mbar + k, 1);
+    }
+    __syncwarp();
+
+    // issue cursor (used by lane 0 only): position of the next chunk to put in flight
+    long long irow = c_begin / p.chunks_per_row;
+    int iidx = (int)(c_begin - irow * p.chunks_per_row);
+    auto issue = [&](int slot) {
+        const long long col0 = (long long)iidx * p.chunk_elems;
+        const long long remain = p.cols - col0;
+        const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+        const int nvec = n_el / VEC;
+        if (nvec > 0) {
+            antq_fence_proxy_async();
+            antq_bulk_g2s(wbase + slot * kChunkBytes, reinterpret_cast<const T *>(p.x) + irow * p.cols + col0,
+                          (unsigned)nvec * 16u, mbar + slot);
+        }
+        if (++iidx == p.chunks_per_row) { iidx = 0; ++irow; }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kRing - 1; k++)
+            if (c_begin + k < c_end) issue(k);
+    }
+
+    // this lane's codebook entries stay in registers for the whole kernel
+    const int nt_real = p.nt_real;
+    const float inf = __int_as_float(0x7f800000);
+    const float tpos = lane < nt_real ? (SYM ? cb->mag_tpos[lane] : cb->thr[lane]) : inf;
+    const float tneg = (SYM && lane < nt_real) ? cb->mag_tneg[lane] : tpos;
+    const float lev = lane <= nt_real ? (SYM ? cb->level[p.mid + lane] : cb->level[lane]) : 0.0f;
+
+    // compute cursor
+    long long row = c_begin / p.chunks_per_row;
+    int idx = (int)(c_begin - row * p.chunks_per_row);
     long long cur_row = -1;
+    float alpha_next = __ldg(p.alpha + (p.alpha_per_row ? row : 0));
     float s = 0.0f;
     bool row_ok = false, row_ties = false;
+    Tables<T, NT, SYM, OVP, CODES> tab;
+    unsigned phases = 0;                      // bit k = parity to wait for on ring slot k
 
-    const long long sg0 = w * p.segs_per_warp;
-    const long long sg1 = (sg0 + p.segs_per_warp) < p.total_segs ? (sg0 + p.segs_per_warp) : p.total_segs;
-    for (long long sg = sg0; sg < sg1; ++sg) {
-        const long long row = sg / p.segs_per_row;
-        const int seg = (int)(sg - row * p.segs_per_row);
+    for (long long c = c_begin; c < c_end; ++c) {
+        const int slot = (int)((c - c_begin) & (kRing - 1));
+        // keep the ring full: the slot freed by the previous iteration receives chunk c + kRing - 1
+        if (lane == 0 && c + (kRing - 1) < c_end) issue((slot + kRing - 1) & (kRing - 1));
+
         if (row != cur_row) {
-            // ---- row prologue: scale, x-space thresholds (lane r <-> threshold r), outputs ----
+            // ---- table rebuild for a new row (copies for this and the next chunks are already in flight) ----
             cur_row = row;
-            const float alpha = __ldg(p.alpha + (p.alpha_per_row ? row : 0));
-            s = __fdiv_rn(alpha, gmax);                          // scale = alpha / max(grid)
-            const bool s_ok = s > 0.0f && s < __int_as_float(0x7f800000);
-            T Xl = A::from_bits(A::kInf), Xnl = A::from_bits(A::kInf), Ol = A::from_bits(0);
-            if (s_ok) {
-                if (lane < nt_real) {
-                    bool near;
-                    if (SYM) {
-                        Xl = antq_x_threshold<T>(cb->mag_tpos[lane], s, &near);
-                        // unless the shortcut proved both sides equal, a negative input can land on the
-                        // other side of a representable tie: give it its own threshold
-                        Xnl = near ? antq_x_threshold_exact<T>(cb->mag_tneg[lane], s) : Xl;
-                    } else {
-                        Xl = antq_x_threshold<T>(cb->thr[lane], s, &near);
+            const float alpha = alpha_next;
+            if (p.alpha_per_row && row + 1 < p.rows) alpha_next = __ldg(p.alpha + row + 1);   // prefetch
+            if (p.debug & 4) {
+                s = 1.0f; row_ok = true; row_ties = false;
+                sX[lane] = sXn[lane] = antq_table_word<T>(A::from_bits(A::kInf));
+                sO[lane] = 0;
+            } else {
+                s = __fdiv_rn(alpha, p.gmax);                          // scale = alpha / max(grid)
+                row_ok = s > 0.0f && s < inf;
+                T Xl = A::from_bits(A::kInf), Xnl = A::from_bits(A::kInf), Ol = A::from_bits(0);
+                if (row_ok) {
+                    if (lane < nt_real) {
+                        bool near;
+                        Xl = antq_x_threshold<T>(tpos, s, &near);
                         Xnl = Xl;
+                        if (SYM && near) {
+                            // a negative input can land on the other side of a representable tie
+                            if constexpr (sizeof(T) == 2) antq_x_threshold16_near<T>(tpos, tneg, s, &Xl, &Xnl);
+                            else Xnl = antq_x_threshold_exact<T>(tneg, s);
+                        }
                     }
+                    if (lane <= nt_real) Ol = A::from_f32_rn(__fmul_rn(lev, s));
                 }
-                if (lane <= nt_real) {
-                    const float lv = SYM ? cb->level[cb->mid + lane] : cb->level[lane];
-                    Ol = A::from_f32_rn(__fmul_rn(lv, s));
-                }
+                row_ties = __any_sync(0xffffffffu, A::bits(Xl) != A::bits(Xnl));
+                sX[lane] = antq_table_word<T>(Xl);
+                sXn[lane] = antq_table_word<T>(Xnl);
+                sO[lane] = antq_table_word<T>(Ol);
             }
-            row_ok = s_ok;
-            row_ties = __any_sync(0xffffffffu, A::bits(Xl) != A::bits(Xnl));
             __syncwarp();
-            sX[wib][lane] = Xl;
-            sXn[wib][lane] = Xnl;
-            sO[wib][lane] = Ol;
+            tab.load(sX, sXn, sO, p.lim, p.ovp_index, s);
             __syncwarp();
-            worker.load(sX[wib], sXn[wib], sO[wib], cb, s);
         }
 
-        const long long col0 = (long long)seg * p.seg_len;
+        const long long col0 = (long long)idx * p.chunk_elems;
         const long long remain = p.cols - col0;
-        const int n_el = (int)(remain < p.seg_len ? remain : p.seg_len);
+        const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
         const int nvec = n_el / VEC;
         const long long base = row * p.cols + col0;
-        const T *xrow = reinterpret_cast<const T *>(p.x) + base;
-        T *orow = reinterpret_cast<T *>(p.out) + base;
-        int16_t *crow = CODES ? p.codes + base : nullptr;
+        const T *xg = reinterpret_cast<const T *>(p.x) + base;
+        T *og = reinterpret_cast<T *>(p.out) + base;
+        int16_t *cg = CODES ? p.codes + base : nullptr;
 
-        if (row_ok) {
-            const bool skipped = row_ties ? worker.template run<true>(cb, xrow, orow, crow, nvec, lane)
-                                          : worker.template run<false>(cb, xrow, orow, crow, nvec, lane);
+        if (nvec > 0) {
+            antq_mbar_wait(mbar + slot, (phases >> slot) & 1u);        // the chunk has landed in shared memory
+            phases ^= 1u << slot;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(wbase + slot * kChunkBytes);
+            bool skipped = !row_ok;
+            if (row_ok)
+                skipped = row_ties ? tab.template chunk<true>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug)
+                                   : tab.template chunk<false>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug);
             if (__any_sync(0xffffffffu, skipped))
-                antq_fixup_pass<T, OVP>(cb, s, worker.xlim_f32(), xrow, orow, crow, nvec, lane);
-        } else {
-            for (int v = lane; v < nvec; v += 32)
-                antq_slow_vec<T, OVP>(cb, s, xrow + (long long)v * VEC, orow + (long long)v * VEC,
-                                      CODES ? crow + (long long)v * VEC : nullptr, VEC);
+                antq_fixup_chunk<T, OVP>(cb, s, tab.xlim_f32(), !row_ok, xg, og, cg, nvec, lane);
         }
         // ragged tail (only a per-tensor view can have one: rows == 1)
         const int tail = n_el - nvec * VEC;
         if (tail > 0 && lane == 0)
-            antq_slow_vec<T, OVP>(cb, s, xrow + (long long)nvec * VEC, orow + (long long)nvec * VEC,
-                                  CODES ? crow + (long long)nvec * VEC : nullptr, tail);
+            antq_slow_vec<T, OVP>(cb, s, xg + (long long)nvec * VEC, og + (long long)nvec * VEC,
+                                  CODES ? cg + (long long)nvec * VEC : nullptr, tail);
+        __syncwarp();                                                  // every lane is done with this slot
+        if (++idx == p.chunks_per_row) { idx = 0; ++row; }
     }
+}
+
+template <typename K> int launch_kernel(K kernel, const RowsParams &p, cudaStream_t st) {
+    const int ctas = (p.total_warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int smem = kWarpsPerCta * kWarpSmemBytes;
+    if (smem > 48 * 1024) {     // opt in beyond the default dynamic-smem limit (idempotent, host-only)
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kernel<<<dim3((unsigned)ctas), dim3(kWarpsPerCta * 32), smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        fprintf(stderr, "antq: rows kernel launch failed: %s (grid %d, block %d, smem %d, chunks %lld)\n",
+                cudaGetErrorString(e), ctas, kWarpsPerCta * 32, smem, p.total_chunks);
+    return (int)e;
 }
 
 template <typename T, int NT, bool SYM, bool OVP>
 int launch_nt(const RowsParams &p, bool codes, cudaStream_t st) {
-    const long long ctas = (p.total_warps + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (ctas > 0x7fffffffLL) return ANTQ_ENOTSUP;
-    dim3 grid((unsigned)ctas), block(kWarpsPerCta * 32);
-    if (codes) antq_rows_kernel<T, NT, SYM, OVP, true><<<grid, block, 0, st>>>(p);
-    else antq_rows_kernel<T, NT, SYM, OVP, false><<<grid, block, 0, st>>>(p);
-    return (int)cudaGetLastError();
+    if (codes) return launch_kernel(antq_rows_kernel<T, NT, SYM, OVP, true>, p, st);
+    return launch_kernel(antq_rows_kernel<T, NT, SYM, OVP, false>, p, st);
 }
 
 template <typename T, bool SYM, bool OVP> int launch_sym(const RowsParams &p, int nt, bool codes, cudaStream_t st) {
@@ -445,36 +515,36 @@ template <typename T> int launch_t(const RowsParams &p, int nt, bool sym, bool o
 
 }  // namespace
 
-// nt = number of thresholds the chain needs (n_mag-1 if symmetric else n_levels-1), known to the host
-// from antq_codebook_info_get at prepare time; sym / ovp likewise.
+// The host knows the codebook header (antq_codebook_info, fetched once at prepare time), so kernel
+// selection and the launch shape need no device round trip.
 int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
-                     long long cols, int dtype, const AntqCodebook *cb, int nt, bool sym, bool ovp,
+                     long long cols, int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp,
                      cudaStream_t st) {
-    const int vec = dtype == ANTQ_F32 ? 4 : 8;
-    // ~16 vectors per lane per segment: enough to amortise the row prologue, small enough to balance 148 SMs
-    const long long target = 32LL * vec * 16;
-    long long segs = (cols + target - 1) / target;
-    if (segs < 1) segs = 1;
-    long long seg_len = (cols + segs - 1) / segs;
-    const long long gran = 32LL * vec;
-    seg_len = (seg_len + gran - 1) / gran * gran;
-    segs = (cols + seg_len - 1) / seg_len;
-    if (segs > 0x7fffffffLL || seg_len > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
+    const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
     RowsParams p;
     p.x = x; p.out = out; p.codes = codes; p.alpha = alpha; p.cb = cb;
-    p.rows = rows; p.cols = cols; p.total_segs = rows * segs;
-    p.alpha_per_row = alpha_per_row; p.segs_per_row = (int)segs; p.seg_len = (int)seg_len;
-    // a warp walks `segs_per_warp` consecutive segments and rebuilds its tables only when the row
-    // changes; cap the grid at ~48 warps per SM worth of work items so long rows / per-tensor
-    // views reuse one prologue for many segments.
-    const long long max_warps = 148LL * 48;
-    long long spw = (p.total_segs + max_warps - 1) / max_warps;
-    if (spw < 1) spw = 1;
-    if (spw > segs) spw = segs;          // never span rows needlessly
-    if (spw > 0x7fffffffLL) return ANTQ_ENOTSUP;
-    p.segs_per_warp = (int)spw;
-    p.total_warps = (p.total_segs + spw - 1) / spw;
-    if (p.total_segs == 0) return 0;
+    p.rows = rows; p.cols = cols;
+    p.chunk_elems = kChunkBytes / es;
+    const long long cpr = (cols + p.chunk_elems - 1) / p.chunk_elems;
+    if (cpr > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    p.chunks_per_row = (int)cpr;
+    p.total_chunks = rows * cpr;
+    if (p.total_chunks == 0) return 0;
+    p.alpha_per_row = alpha_per_row;
+    // persistent grid: every warp slot of the machine, fewer only when there are fewer chunks than slots
+    const int regs_ctas = nt <= 7 ? kCtasPerSm : (nt <= 15 ? 3 : 2);
+    long long warps = (long long)kNumSms * regs_ctas * kWarpsPerCta;
+    if (warps > p.total_chunks) warps = (p.total_chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+    p.total_warps = (int)warps;
+    p.nt_real = nt; p.mid = info->mid; p.ovp_index = info->ovp_index; p.n_entries = info->n_entries;
+    p.gmax = info->gmax; p.lim = info->lim;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("ANTQ_DEBUG"); dbg = e ? atoi(e) : 0; }
+        p.debug = dbg;
+    }
     switch (dtype) {
         case ANTQ_F32: return launch_t<float>(p, nt, sym, ovp, codes != nullptr, st);
         case ANTQ_F16: return launch_t<__half>(p, nt, sym, ovp, codes != nullptr, st);
