@@ -9,7 +9,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_PKG, "csrc", "libantq.so")
+SO_PATH = os.path.join(_PKG, "csrc", "libantq%s.so" % os.environ.get("ANTQ_LIB_SUFFIX", ""))   # suffix: tuning builds only
 
 F32, F16, BF16 = 0, 1, 2
 FLAG_OVP, FLAG_FORCE_FLAT, FLAG_FORCE_ROWS = 1, 2, 4

@@ -13,13 +13,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(CSRC, "libantq.so")
+SUFFIX = os.environ.get("ANTQ_LIB_SUFFIX", "")
+OUT = os.path.join(CSRC, "libantq%s.so" % SUFFIX)
 SOURCES = ["antq_prepare.cu", "antq_rows.cu", "antq_flat.cu", "antq_capi.cu", "antq_debug.cu"]
 HEADERS = ["antq_common.cuh", os.path.join("..", "..", "include", "antq.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--ftz=false", "--prec-div=true", "--prec-sqrt=true", "--fmad=false",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + os.environ.get("ANTQ_EXTRA_DEFS", "").split()
 
 
 def _stale():
@@ -31,7 +32,7 @@ def _stale():
 
 
 def _compile(src):
-    obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+    obj = os.path.join(CSRC, src.replace(".cu", SUFFIX + ".o"))
     cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

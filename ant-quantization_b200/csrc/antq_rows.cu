@@ -15,15 +15,17 @@
 // Values outside the window, NaN/Inf and rows whose scale is not a positive finite
 // number take the literal reference arithmetic (antq_slow_vec): rare, exact.
 //
-// Execution shape (B200): a PERSISTENT grid of 148 x 4 CTAs x 4 warps.  The tensor
-// is cut into 2 KiB chunks that never straddle a row; every warp owns an equal,
+// Execution shape (B200): a PERSISTENT grid of 148 x 3 CTAs x 4 warps.  The tensor
+// is cut into 4 KiB chunks that never straddle a row; every warp owns an equal,
 // contiguous range of chunks (static balance, no tail wave) and walks it with a
-// 4-deep ring of TMA bulk copies (cp.async.bulk -> shared memory, completion on an
-// mbarrier), so up to 6 KiB per warp / 96 KiB per SM are in flight without holding
-// registers.  When the row changes the warp rebuilds its (X, O) tables: lane r owns
-// threshold r, its codebook values stay in registers for the whole kernel and the
-// next row's alpha is prefetched, so the rebuild is ~60 instructions off the
-// critical path of the copies already in flight.
+// double-buffered ring of TMA bulk copies (cp.async.bulk -> shared memory, completion
+// on an mbarrier), so the next chunk is in flight while the current one is computed,
+// without holding registers.  When the row changes the warp rebuilds its tables: lane r
+// owns threshold r, its codebook values stay in registers for the whole kernel and the
+// next row's alpha is prefetched.  Half of the pairs use the ALU-pipe formulation
+// (HSET2 + LOP3), the other half an exact FMA-pipe formulation (HFMA2.SAT compare +
+// HFMA2 accumulate), because both pipes are half-rate and the ALU pipe alone was the
+// limiter (profiles/).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -31,15 +33,27 @@
 
 namespace {
 
+#ifndef ANTQ_FMA_PAIRS
+#define ANTQ_FMA_PAIRS 2      // pairs per vector (of 4) that take the FMA-pipe formulation
+#endif
+#ifndef ANTQ_LOOP_VECS
+#define ANTQ_LOOP_VECS 2      // vectors per lane per loop iteration
+#endif
 constexpr int kWarpsPerCta = 4;
 constexpr int kCtasPerSm = 3;
 constexpr int kNumSms = 148;
-constexpr int kRing = 8;                 // chunks in flight + in use per warp
-constexpr int kChunkBytes = 2048;        // one chunk = 128 vectors = 4 per lane
+#ifndef ANTQ_RING
+#define ANTQ_RING 2      // measured best on 4096x4096 fp16 (profiles/r01_tuning.md): deeper rings front-load the
+#endif                   // whole tensor's requests and delay each warp's first chunk
+#ifndef ANTQ_CHUNK
+#define ANTQ_CHUNK 4096
+#endif
+constexpr int kRing = ANTQ_RING;         // chunks in flight + in use per warp (power of two)
+constexpr int kChunkBytes = ANTQ_CHUNK;  // 4096 = 256 vectors = 8 per lane
 constexpr int kChunkVecs = kChunkBytes / 16;
 constexpr int kVecPerLane = kChunkVecs / 32;
 constexpr int kTableWords = 32;          // per table, per warp (uint32 / float)
-constexpr int kWarpSmemBytes = kRing * kChunkBytes + 3 * kTableWords * 4 + 128;   // ring | X | Xn | O | mbarriers
+constexpr int kWarpSmemBytes = kRing * kChunkBytes + 6 * kTableWords * 4 + 128;   // ring | X | Xn | O | B | C | D | mbarriers
 
 template <typename T, bool OVP>
 __device__ __noinline__ void antq_slow_vec(const AntqCodebook *__restrict__ cb, float s, const T *xg, T *og,
@@ -129,6 +143,35 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct Tables {
                           // (ties go to the LATER grid entry: up for positive d, toward zero for negative d)
     uint32_t O[NT + 1];   // dequantised outputs per level / magnitude
     uint32_t xlim, xovp, xovpn;
+    // FMA-pipe twin of the compare (16-bit types): with P = prev(X), u = X - P (a power of two),
+    //   m = sat((S*a) * (1/(u*S)) - P/u)  is exactly 1.0 for a >= X and exactly 0.0 for a <= P,
+    // because the fused product-sum is <= 0 or >= 1 before its single rounding.  S = 2^k keeps 1/(u*S) in range.
+    uint32_t Bf[IS16 ? NT : 1];   // 1/(u*S), duplicated
+    uint32_t Cf[IS16 ? NT : 1];   // -P/u,    duplicated
+    uint32_t Df[IS16 ? NT : 1];   // O[i+1] - O[i]: exactly representable when successive outputs are within 2x
+                                  // (checked per row), so q <- m*D + q reproduces O[rank] without rounding
+    uint32_t S2;
+
+    __device__ __forceinline__ void load_fma(const uint32_t *sB, const uint32_t *sC, const uint32_t *sD, uint32_t s2) {
+        if constexpr (IS16) {
+            constexpr int NX = (NT + 3) / 4;
+            uint4 bb[NX], bc[NX], bd[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                bb[i] = reinterpret_cast<const uint4 *>(sB)[i];
+                bc[i] = reinterpret_cast<const uint4 *>(sC)[i];
+                bd[i] = reinterpret_cast<const uint4 *>(sD)[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NT; i++) {
+                const uint4 a = bb[i / 4], b = bc[i / 4], c = bd[i / 4];
+                Bf[i] = (i % 4 == 0) ? a.x : (i % 4 == 1) ? a.y : (i % 4 == 2) ? a.z : a.w;
+                Cf[i] = (i % 4 == 0) ? b.x : (i % 4 == 1) ? b.y : (i % 4 == 2) ? b.z : b.w;
+                Df[i] = (i % 4 == 0) ? c.x : (i % 4 == 1) ? c.y : (i % 4 == 2) ? c.z : c.w;
+            }
+            S2 = s2;
+        }
+    }
 
     __device__ __forceinline__ void load(const uint32_t *sX, const uint32_t *sXn, const uint32_t *sO, float lim, int oi,
                                          float s) {
@@ -199,6 +242,42 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct Tables {
         return q;
     }
 
+    // The same pair on the FMA pipe (tie-free rows, no codes): saturating-FMA compares and an exact
+    // accumulation  q <- m*D_i + q  with m in {0, 1}; only the window test, the sign and the OVP
+    // mask stay on the ALU pipe.  Interleaved with pair<>() so that both half-rate pipes are busy.
+    __device__ __forceinline__ uint32_t pair_fma(uint32_t xb, bool &special, uint32_t &victims) const {
+        typedef typename Pack2<T>::v2 v2;
+        const v2 x2 = Pack2<T>::from_u32(xb);
+        const v2 ab = __habs2(x2);
+        special |= (__hle2_mask(ab, Pack2<T>::from_u32(xlim)) != 0xffffffffu);
+        const v2 xs = __hmul2(SYM ? ab : x2, Pack2<T>::from_u32(S2));
+        v2 q = Pack2<T>::from_u32(O[0]);
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            const v2 m = __hfma2_sat(xs, Pack2<T>::from_u32(Bf[i]), Pack2<T>::from_u32(Cf[i]));
+            q = __hfma2(m, Pack2<T>::from_u32(Df[i]), q);
+        }
+        uint32_t qb;
+        if (SYM) {
+            // (+-1) * q + 0: restores the sign and leaves a zero level at +0
+            const uint32_t one = IS16 && sizeof(T) == 2 ? (AntqType<T>::kInf == 0x7c00u ? 0x3c003c00u : 0x3f803f80u) : 0u;
+            const v2 sg = Pack2<T>::from_u32((xb & 0x80008000u) | one);
+            const v2 r = __hfma2(q, sg, Pack2<T>::from_u32(0u));
+            qb = *reinterpret_cast<const uint32_t *>(&r);
+        } else {
+            qb = *reinterpret_cast<const uint32_t *>(&q);
+        }
+        if (OVP) {
+            const v2 a2 = SYM ? ab : x2;
+            const uint32_t mo = __hge2_mask(a2, Pack2<T>::from_u32(xovp));
+            const uint32_t sw = __byte_perm(mo, 0, 0x1032);
+            const uint32_t kill = sw & ~(mo & 0x0000ffffu);
+            qb &= ~kill;
+            victims = kill;
+        }
+        return qb;
+    }
+
     // fp32: one element per register; fp32 x-space resolves ties, so negatives always use Xn
     __device__ __forceinline__ float one(float x, bool &special, int &rank, bool &outlier) const {
         const float a = SYM ? fabsf(x) : x;
@@ -220,92 +299,115 @@ template <typename T, int NT, bool SYM, bool OVP, bool CODES> struct Tables {
         return q;
     }
 
-    // One chunk (<= 4 vectors per lane) from shared memory to global.  Returns true if this lane
-    // skipped a vector (left for antq_fixup_chunk).
-    template <bool TIES>
+    // One vector (8 x 16-bit or 4 x fp32 elements) of this lane; returns false if it must go to the slow path.
+    template <bool TIES, bool FMA>
+    __device__ __forceinline__ bool vec(const AntqCodebook *__restrict__ cb, const uint4 r, uint4 *dst, int16_t *cdst,
+                                        int mid, int K, int dbg) const {
+        bool special = false;
+        uint4 q;
+        if constexpr (IS16) {
+            uint32_t rk[4] = {0, 0, 0, 0}, vi[4] = {0, 0, 0, 0};
+            if (dbg & 2) {
+                q = r;
+            } else {
+                constexpr bool F = FMA && !TIES && !CODES;
+                q.x = pair<TIES>(r.x, special, rk[0], vi[0]);
+                if constexpr (F && ANTQ_FMA_PAIRS >= 3) q.z = pair_fma(r.z, special, vi[2]);
+                else q.z = pair<TIES>(r.z, special, rk[2], vi[2]);
+                if constexpr (F) {
+                    q.y = pair_fma(r.y, special, vi[1]);
+                    q.w = pair_fma(r.w, special, vi[3]);
+                } else {
+                    q.y = pair<TIES>(r.y, special, rk[1], vi[1]);
+                    q.w = pair<TIES>(r.w, special, rk[3], vi[3]);
+                }
+            }
+            if ((dbg & 1) && q.x != 0x12345678u) return !special;
+            if (!special) {
+                antq_stg_stream(dst, q);
+                if (CODES) {
+                    const uint32_t xb[4] = {r.x, r.y, r.z, r.w};
+                    __align__(16) int16_t cc[8];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        cc[2 * k] = antq_rank_to_code<SYM>(cb, mid, rk[k] & 0xffff, (xb[k] & 0x8000u) != 0);
+                        cc[2 * k + 1] = antq_rank_to_code<SYM>(cb, mid, rk[k] >> 16, (xb[k] & 0x80000000u) != 0);
+                        if (OVP && (vi[k] & 0xffffu)) cc[2 * k] = (int16_t)K;
+                        if (OVP && (vi[k] >> 16)) cc[2 * k + 1] = (int16_t)K;
+                    }
+                    *reinterpret_cast<uint4 *>(cdst) = *reinterpret_cast<uint4 *>(cc);
+                }
+            }
+        } else {
+            const float xv[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
+            float qv[4];
+            int rk[4];
+            bool ol[4] = {false, false, false, false}, vict[4] = {false, false, false, false};
+#pragma unroll
+            for (int k = 0; k < 4; k++) qv[k] = one(xv[k], special, rk[k], ol[k]);
+            if (OVP) {
+#pragma unroll
+                for (int k = 0; k < 4; k += 2) {
+                    vict[k + 1] = ol[k];
+                    vict[k] = ol[k + 1] && !ol[k];
+                    if (vict[k]) qv[k] = 0.0f;
+                    if (vict[k + 1]) qv[k + 1] = 0.0f;
+                }
+            }
+            if (!special) {
+                q = make_uint4(__float_as_uint(qv[0]), __float_as_uint(qv[1]), __float_as_uint(qv[2]),
+                               __float_as_uint(qv[3]));
+                antq_stg_stream(dst, q);
+                if (CODES) {
+                    __align__(8) int16_t cc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        cc[k] = antq_rank_to_code<SYM>(cb, mid, rk[k], (__float_as_uint(xv[k]) >> 31) != 0);
+                        if (OVP && vict[k]) cc[k] = (int16_t)K;
+                    }
+                    *reinterpret_cast<uint2 *>(cdst) = *reinterpret_cast<uint2 *>(cc);
+                }
+            }
+        }
+        return !special;
+    }
+
+    // One chunk (<= 4 vectors per lane) from shared memory to global, as a ROLLED loop with the next
+    // vector's LDS issued ahead (three code paths x four unrolled vectors overflowed the 32 KiB
+    // instruction cache and the register file).  Returns true if this lane skipped a vector.
+    template <bool TIES, bool FMA>
     __device__ __forceinline__ bool chunk(const AntqCodebook *__restrict__ cb, const uint4 *sv, T *og, int16_t *cg,
                                           int nvec, int lane, int mid, int K, int dbg) const {
         constexpr int VEC = AntqType<T>::kVec;
         uint4 *oout = reinterpret_cast<uint4 *>(og);
-        bool any_special = false;
-        uint4 r[kVecPerLane];
+        bool skipped = false;
+        constexpr int LV = ANTQ_LOOP_VECS;
+        uint4 cur[LV];
 #pragma unroll
-        for (int j = 0; j < kVecPerLane; j++) {
-            const int v = j * 32 + lane;
-            if (v < nvec) r[j] = sv[v];                       // LDS.128, conflict free
+        for (int u = 0; u < LV; u++) {
+            cur[u] = make_uint4(0, 0, 0, 0);
+            if (lane + 32 * u < nvec) cur[u] = sv[lane + 32 * u];           // LDS.128, conflict free
         }
+#pragma unroll 1
+        for (int v = lane; v < nvec; v += 32 * LV) {
+            uint4 nxt[LV];
 #pragma unroll
-        for (int j = 0; j < kVecPerLane; j++) {
-            const int v = j * 32 + lane;
-            if (v < nvec) {
-                bool special = false;
-                uint4 q;
-                if constexpr (IS16) {
-                    uint32_t rk[4] = {0, 0, 0, 0}, vi[4] = {0, 0, 0, 0};
-                    if (dbg & 2) {
-                        q = r[j];
-                    } else {
-                        q.x = pair<TIES>(r[j].x, special, rk[0], vi[0]);
-                        q.y = pair<TIES>(r[j].y, special, rk[1], vi[1]);
-                        q.z = pair<TIES>(r[j].z, special, rk[2], vi[2]);
-                        q.w = pair<TIES>(r[j].w, special, rk[3], vi[3]);
-                    }
-                    any_special |= special;
-                    if ((dbg & 1) && q.x != 0x12345678u) continue;
-                    if (!special) {
-                        antq_stg_stream(oout + v, q);
-                        if (CODES) {
-                            const uint32_t xb[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-                            __align__(16) int16_t cc[8];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                cc[2 * k] = antq_rank_to_code<SYM>(cb, mid, rk[k] & 0xffff, (xb[k] & 0x8000u) != 0);
-                                cc[2 * k + 1] =
-                                    antq_rank_to_code<SYM>(cb, mid, rk[k] >> 16, (xb[k] & 0x80000000u) != 0);
-                                if (OVP && (vi[k] & 0xffffu)) cc[2 * k] = (int16_t)K;
-                                if (OVP && (vi[k] >> 16)) cc[2 * k + 1] = (int16_t)K;
-                            }
-                            *reinterpret_cast<uint4 *>(cg + (long long)v * VEC) = *reinterpret_cast<uint4 *>(cc);
-                        }
-                    }
-                } else {
-                    const float xv[4] = {__uint_as_float(r[j].x), __uint_as_float(r[j].y), __uint_as_float(r[j].z),
-                                         __uint_as_float(r[j].w)};
-                    float qv[4];
-                    int rk[4];
-                    bool ol[4] = {false, false, false, false}, vict[4] = {false, false, false, false};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) qv[k] = one(xv[k], special, rk[k], ol[k]);
-                    if (OVP) {
-#pragma unroll
-                        for (int k = 0; k < 4; k += 2) {
-                            vict[k + 1] = ol[k];
-                            vict[k] = ol[k + 1] && !ol[k];
-                            if (vict[k]) qv[k] = 0.0f;
-                            if (vict[k + 1]) qv[k + 1] = 0.0f;
-                        }
-                    }
-                    any_special |= special;
-                    if (!special) {
-                        q = make_uint4(__float_as_uint(qv[0]), __float_as_uint(qv[1]), __float_as_uint(qv[2]),
-                                       __float_as_uint(qv[3]));
-                        antq_stg_stream(oout + v, q);
-                        if (CODES) {
-                            __align__(8) int16_t cc[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                cc[k] = antq_rank_to_code<SYM>(cb, mid, rk[k], (__float_as_uint(xv[k]) >> 31) != 0);
-                                if (OVP && vict[k]) cc[k] = (int16_t)K;
-                            }
-                            *reinterpret_cast<uint2 *>(cg + (long long)v * VEC) = *reinterpret_cast<uint2 *>(cc);
-                        }
-                    }
-                }
+            for (int u = 0; u < LV; u++) {
+                nxt[u] = make_uint4(0, 0, 0, 0);
+                if (v + 32 * (LV + u) < nvec) nxt[u] = sv[v + 32 * (LV + u)];
             }
+#pragma unroll
+            for (int u = 0; u < LV; u++)
+                if (u == 0 || v + 32 * u < nvec)
+                    skipped |= !vec<TIES, FMA>(cb, cur[u], oout + v + 32 * u,
+                                               CODES ? cg + (long long)(v + 32 * u) * VEC : nullptr, mid, K, dbg);
+#pragma unroll
+            for (int u = 0; u < LV; u++) cur[u] = nxt[u];
         }
-        return any_special;
+        return skipped;
     }
 };
+
 
 struct RowsParams {
     const void *x;
@@ -355,7 +457,10 @@ antq_rows_kernel(const RowsParams p) {
     uint32_t *sX = reinterpret_cast<uint32_t *>(wbase + kRing * kChunkBytes);
     uint32_t *sXn = sX + kTableWords;
     uint32_t *sO = sXn + kTableWords;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sO + kTableWords);
+    uint32_t *sB = sO + kTableWords;
+    uint32_t *sC = sB + kTableWords;
+    uint32_t *sD = sC + kTableWords;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sD + kTableWords);
 
     const int w = blockIdx.x * kWarpsPerCta + wib;
     // equal contiguous share of the chunk list
@@ -404,7 +509,7 @@ antq_rows_kernel(const RowsParams p) {
     long long cur_row = -1;
     float alpha_next = __ldg(p.alpha + (p.alpha_per_row ? row : 0));
     float s = 0.0f;
-    bool row_ok = false, row_ties = false;
+    bool row_ok = false, row_ties = false, row_fma = false;
     Tables<T, NT, SYM, OVP, CODES> tab;
     unsigned phases = 0;                      // bit k = parity to wait for on ring slot k
 
@@ -443,9 +548,54 @@ antq_rows_kernel(const RowsParams p) {
                 sX[lane] = antq_table_word<T>(Xl);
                 sXn[lane] = antq_table_word<T>(Xnl);
                 sO[lane] = antq_table_word<T>(Ol);
+                // FMA-pipe twin tables (16-bit types, tie-free rows)
+                uint32_t s2 = 0;
+                row_fma = false;
+                if constexpr (sizeof(T) == 2) {
+                    if (row_ok && !row_ties && !(p.debug & 16)) {
+                        // S = 2^k with xlim * S in [2^13, 2^14): every in-window |x| stays finite after scaling
+                        const float xl = __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);
+                        int k = 13 - (int)((__float_as_uint(xl) >> 23) & 0xff) + 127;
+                        k = k > 15 ? 15 : (k < -14 ? -14 : k);
+                        const float S = __uint_as_float((unsigned)(127 + k) << 23);
+                        bool ok = isfinite(A::to_f32(Ol));
+                        float Bv = 0.0f, Cv = -1.0f;              // padding: m = sat(0 * xs - 1) = 0
+                        if (lane < nt_real) {
+                            const T P = antq_next_down(Xl);
+                            if (antq_is_inf(Xl)) {
+                                Bv = 0.0f; Cv = -1.0f;                                   // never reached
+                            } else if (antq_is_inf(P)) {
+                                Bv = 0.0f; Cv = 1.0f;                                    // always reached
+                            } else {
+                                const float u = __fsub_rn(A::to_f32(Xl), A::to_f32(P));  // exact power of two
+                                const int eu = (int)((__float_as_uint(u) >> 23) & 0xff);       // u is a normal fp32
+                                const float Bfull = __uint_as_float((unsigned)(254 - eu) << 23);                // 1 / u
+                                const int eb = 254 - eu - k;
+                                Bv = (eb >= 1 && eb <= 254) ? __uint_as_float((unsigned)eb << 23) : 0.0f;      // 1 / (u S)
+                                Cv = -__fmul_rn(A::to_f32(P), Bfull);
+                                ok = ok && Bv >= 6.103515625e-05f && Bv <= 32768.0f && fabsf(Cv) <= 2048.0f;
+                            }
+                        }
+                        // D_i = O[i+1] - O[i] must be exactly representable (fp32 difference of two 16-bit values is exact)
+                        const float o_next = __shfl_down_sync(0xffffffffu, A::to_f32(Ol), 1);
+                        const float dex = __fsub_rn(o_next, A::to_f32(Ol));
+                        const T D = A::from_f32_rn(dex);
+                        if (lane < nt_real) ok = ok && (A::to_f32(D) == dex);
+                        sD[lane] = antq_table_word<T>(lane < nt_real ? D : A::from_bits(0));
+                        sB[lane] = antq_table_word<T>(A::from_f32_rn(Bv));
+                        sC[lane] = antq_table_word<T>(A::from_f32_rn(Cv));
+                        s2 = antq_table_word<T>(A::from_f32_rn(S));
+                        row_fma = __all_sync(0xffffffffu, ok);
+                    }
+                }
+                __syncwarp();
+                tab.load(sX, sXn, sO, p.lim, p.ovp_index, s);
+                if (row_fma) tab.load_fma(sB, sC, sD, s2);
             }
-            __syncwarp();
-            tab.load(sX, sXn, sO, p.lim, p.ovp_index, s);
+            if (p.debug & 4) {
+                __syncwarp();
+                tab.load(sX, sXn, sO, p.lim, p.ovp_index, s);
+            }
             __syncwarp();
         }
 
@@ -464,8 +614,9 @@ antq_rows_kernel(const RowsParams p) {
             const uint4 *sv = reinterpret_cast<const uint4 *>(wbase + slot * kChunkBytes);
             bool skipped = !row_ok;
             if (row_ok)
-                skipped = row_ties ? tab.template chunk<true>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug)
-                                   : tab.template chunk<false>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug);
+                skipped = row_ties  ? tab.template chunk<true, false>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug)
+                          : row_fma ? tab.template chunk<false, true>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug)
+                                    : tab.template chunk<false, false>(cb, sv, og, cg, nvec, lane, p.mid, p.n_entries, p.debug);
             if (__any_sync(0xffffffffu, skipped))
                 antq_fixup_chunk<T, OVP>(cb, s, tab.xlim_f32(), !row_ok, xg, og, cg, nvec, lane);
         }
