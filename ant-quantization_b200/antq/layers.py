@@ -1,0 +1,177 @@
+"""Quantized layer wrappers of antquant on top of the fused quantizer.
+
+Each wrapper owns two TensorQuantizers and re-fake-quantizes weight and input on every
+forward, exactly like the reference (A/antquant/quant_modules.py:582-646,
+O/antquant/quant_modules.py:358-450, A/antquant/multihead_attention.py:486-687); the
+matmul / conv itself stays a stock PyTorch op.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _copy_param(t):
+    return None if t is None else nn.Parameter(t.data.clone())
+
+
+def make_layers(TensorQuantizer):
+    """Build the wrapper classes for one flavour of TensorQuantizer."""
+
+    class _TwoQuantizers(nn.Module):
+        def __init__(self, mode=None, wbit=None, abit=None, args=None):
+            super().__init__()
+            assert mode is not None, 'Quantizer is not initilized!'
+            op = self._op_handle()
+            self.quant_weight = TensorQuantizer(mode=mode, bit=wbit, is_signed=True, is_enable=True, args=args,
+                                                operator=op)
+            self.quant_input = TensorQuantizer(mode=mode, bit=abit, is_signed=False, is_enable=True, args=args,
+                                               operator=op, is_input=True)
+
+        def _op_handle(self):
+            return None
+
+        def _set_weight_bias(self, src):
+            self.weight = _copy_param(src.weight)
+            self.bias = _copy_param(getattr(src, "bias", None))
+
+        def _quantized(self, input):
+            weight = self.quant_weight(self.weight, input)
+            input = self.quant_input(input, self.weight)
+            return input, weight
+
+    class Conv2dQuantizer(_TwoQuantizers):
+        """Class to quantize given convolutional layer"""
+
+        def _op_handle(self):
+            return self._conv_forward
+
+        def set_param(self, conv):
+            for k in ("in_channels", "out_channels", "kernel_size", "stride", "padding", "dilation", "groups"):
+                setattr(self, k, getattr(conv, k))
+            self.quant_weight.alpha.data = torch.ones([self.out_channels, 1])
+            self._set_weight_bias(conv)
+
+        def _conv_forward(self, input, weight):
+            return F.conv2d(input, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+        def forward(self, input):
+            input, weight = self._quantized(input)
+            return self._conv_forward(input, weight)
+
+    class LinearQuantizer(_TwoQuantizers):
+        """Class to quantize given linear layer"""
+
+        def _op_handle(self):
+            return F.linear
+
+        def set_param(self, linear):
+            self.in_features = linear.in_features
+            self.out_features = linear.out_features
+            self.quant_weight.alpha.data = torch.ones([self.out_features, 1])
+            self._set_weight_bias(linear)
+
+        def forward(self, input):
+            input, weight = self._quantized(input)
+            return F.linear(input, weight, self.bias)
+
+    class Conv1dQuantizer(_TwoQuantizers):
+        """HF GPT-2 style Conv1D (weight is [in, out]; per-'channel' scale follows dim 0 as in the reference)"""
+
+        def _op_handle(self):
+            return self._conv_forward
+
+        def set_param(self, conv):
+            self.nf = conv.nf
+            self._set_weight_bias(conv)
+
+        def _conv_forward(self, x, weight):
+            size_out = x.size()[:-1] + (self.nf,)
+            return torch.addmm(self.bias, x.view(-1, x.size(-1)), weight).view(size_out)
+
+        def forward(self, input):
+            input, weight = self._quantized(input)
+            return self._conv_forward(input, weight)
+
+    class MultiheadAttentionQuantizer(nn.Module):
+        """Self-attention with fake-quantized in/out projections (torchvision ViT).  As in the
+        reference, key and value are REPLACED by the quantized query (A/...multihead_attention.py:663-666),
+        all four quantizers are signed, and the out-projection input is quantized after the head merge (:459)."""
+
+        def __init__(self, mode=None, wbit=None, abit=None, args=None):
+            super().__init__()
+            assert mode is not None, 'Quantizer is not initilized!'
+            kw = dict(mode=mode, is_signed=True, is_enable=True, args=args)
+            self.in_quant_weight = TensorQuantizer(bit=wbit, **kw)
+            self.in_quant_input = TensorQuantizer(bit=abit, is_input=True, **kw)
+            self.out_quant_weight = TensorQuantizer(bit=wbit, **kw)
+            self.out_quant_input = TensorQuantizer(bit=abit, is_input=True, **kw)
+
+        def set_param(self, MA):
+            self.embed_dim, self.num_heads, self.dropout = MA.embed_dim, MA.num_heads, MA.dropout
+            self.kdim, self.vdim, self.batch_first = MA.kdim, MA.vdim, MA.batch_first
+            self._qkv_same_embed_dim = self.kdim == self.embed_dim and self.vdim == self.embed_dim
+            if not self._qkv_same_embed_dim:
+                raise NotImplementedError("MultiheadAttentionQuantizer: packed in_proj (kdim == vdim == embed_dim) only")
+            self.head_dim = self.embed_dim // self.num_heads
+            assert self.head_dim * self.num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
+            self.add_zero_attn = MA.add_zero_attn
+            self.in_quant_weight.alpha.data = torch.ones([self.embed_dim * 3, 1])
+            self.out_quant_weight.alpha.data = torch.ones([self.embed_dim, 1])
+            self.in_proj_weight = _copy_param(MA.in_proj_weight)
+            self.in_proj_bias = _copy_param(MA.in_proj_bias)
+            self.out_proj_weight = _copy_param(MA.out_proj.weight)
+            self.out_proj_bias = _copy_param(MA.out_proj.bias)
+            self.bias_k = _copy_param(MA.bias_k)
+            self.bias_v = _copy_param(MA.bias_v)
+            if self.bias_k is not None or self.add_zero_attn:
+                raise NotImplementedError("MultiheadAttentionQuantizer: bias_k/bias_v/add_zero_attn are not supported")
+
+        def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=True, attn_mask=None,
+                    average_attn_weights=True):
+            w_in = self.in_quant_weight(self.in_proj_weight)
+            x = self.in_quant_input(query)
+            w_out = self.out_quant_weight(self.out_proj_weight)
+            batched = x.dim() == 3
+            if not batched:
+                x = x.unsqueeze(1)
+            elif self.batch_first:
+                x = x.transpose(0, 1)
+            L, N, E = x.shape                                            # (seq, batch, embed)
+            q, k, v = F.linear(x, w_in, self.in_proj_bias).chunk(3, dim=-1)
+            heads = lambda t: t.contiguous().view(L, N * self.num_heads, self.head_dim).transpose(0, 1)
+            q, k, v = heads(q), heads(k), heads(v)
+            mask = None
+            if attn_mask is not None:
+                mask = attn_mask
+                if mask.dtype == torch.bool:
+                    mask = torch.zeros_like(mask, dtype=q.dtype).masked_fill_(mask, float("-inf"))
+                if mask.dim() == 2:
+                    mask = mask.unsqueeze(0)
+            if key_padding_mask is not None:
+                kpm = key_padding_mask.view(N, 1, 1, L).expand(-1, self.num_heads, -1, -1).reshape(N * self.num_heads, 1, L)
+                if kpm.dtype == torch.bool:
+                    kpm = torch.zeros_like(kpm, dtype=q.dtype).masked_fill_(kpm, float("-inf"))
+                mask = kpm if mask is None else mask + kpm
+            scores = torch.bmm(q / math.sqrt(self.head_dim), k.transpose(-2, -1))
+            if mask is not None:
+                scores = scores + mask
+            attn = F.softmax(scores, dim=-1)
+            if self.training and self.dropout > 0.0:
+                attn = F.dropout(attn, p=self.dropout)
+            ctx = torch.bmm(attn, v).transpose(0, 1).contiguous().view(L, N, E)
+            out = F.linear(self.out_quant_input(ctx), w_out, self.out_proj_bias)
+            weights = None
+            if need_weights:
+                weights = attn.view(N, self.num_heads, L, L)
+                if average_attn_weights:
+                    weights = weights.sum(dim=1) / self.num_heads
+            if not batched:
+                out = out.squeeze(1)
+                weights = None if weights is None else weights.squeeze(0)
+            elif self.batch_first:
+                out = out.transpose(0, 1)
+            return out, weights
+
+    return Conv2dQuantizer, LinearQuantizer, Conv1dQuantizer, MultiheadAttentionQuantizer

@@ -1,0 +1,429 @@
+"""The `Quantizer` / `TensorQuantizer` of antquant, backed by the fused sm_100a kernels.
+
+Mirror of the reference worker classes (same constructor, attributes, buffers and
+method names, so `quant_model.py` / `quant_utils.py` style code and checkpoints keep
+working) with the arithmetic moved into libantq.so:
+
+  reference                                             here
+  QuantBase._quantization + quant_cuda.quant            antq.lut_nearest            (A/antquant/quant_modules.py:11-24)
+  Quantizer._forward (7 elementwise passes + scan)      ONE antq_fakequant launch   (A/...:535-551, O/...:295-330)
+  search_mse (75-88 x ~20 passes)                       ONE antq_mse_sweep launch   (A/...:287-326, O/...:190-233)
+  abs-max init                                          antq_absmax                 (A/...:473-477)
+
+Two flavours share the class: "ant" (A/antquant/quant_modules.py) and "olive"
+(O/antquant/quant_modules.py: threshold-32 grids, abfloat outliers, 3-sigma alpha
+init, outlier-victim pairs, everything under no_grad).
+
+There is no CPU arithmetic path: a quantizer that is enabled raises on CPU tensors.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import codebooks, ops
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized()
+
+
+def _rank0():
+    return (not _dist_on()) or dist.get_rank() == 0
+
+
+class _FakeQuantSTE(torch.autograd.Function):
+    """out = ((q - d).detach() + d) * s with d = x / s, s = alpha / max(grid)  (A/...:535-551).
+    d out/d x = 1 (also for clipped elements); d out/d alpha = sum(g * (q - d)) / max(grid)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, quantizer):
+        out = quantizer._launch(x, alpha)
+        ctx.quantizer = quantizer
+        ctx.alpha_shape = alpha.shape
+        ctx.save_for_backward(x, out, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, alpha = ctx.saved_tensors
+        q = ctx.quantizer
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            # mathematically g; the reference's autograd produces fl(fl(g * s) / s) (mul then div), kept bit for bit
+            gmax0 = q._grid_max()
+            if q.is_perchannel:
+                s0 = alpha.reshape(x.shape[0], 1) / gmax0
+                grad_x = ((g.reshape(x.shape[0], -1) * s0) / s0).view(g.shape)
+            else:
+                s0 = alpha / gmax0
+                grad_x = (g * s0) / s0
+        grad_alpha = None
+        if ctx.needs_input_grad[1]:
+            gmax = q._grid_max()
+            if q.is_perchannel:
+                rows = x.shape[0]
+                s = (alpha.reshape(rows, 1).float() / gmax)
+                qd = (out.reshape(rows, -1).float() - x.reshape(rows, -1).float()) / s      # q - d
+                grad_alpha = ((g.reshape(rows, -1).float() * qd).sum(1) / gmax).reshape(ctx.alpha_shape)
+            else:
+                s = alpha.float() / gmax
+                qd = (out.float() - x.float()) / s
+                grad_alpha = ((g.float() * qd).sum() / gmax).reshape(ctx.alpha_shape)
+            grad_alpha = grad_alpha.to(alpha.dtype)
+        return grad_x, grad_alpha, None
+
+
+class QuantBase:
+    """quant_cuda.quant behind the reference's static helper (A/antquant/quant_modules.py:11-24)."""
+
+    @staticmethod
+    def _quantization(x, quant_grid):
+        cb = ops.prepare_codebook(quant_grid.to(x.device))
+        flat = x.reshape(-1)
+        if flat.dtype == torch.float64:                      # the kernel narrows doubles to float (quant_kernel.cu:28)
+            return ops.lut_nearest(flat.float().contiguous(), cb).double().view(x.shape)
+        return ops.lut_nearest(flat.contiguous(), cb).view(x.shape)
+
+    @staticmethod
+    def forward(real_val, quant_grid):
+        with torch.no_grad():
+            return QuantBase._quantization(real_val, quant_grid)
+
+
+class Quantizer(nn.Module):
+    flavor = "ant"
+
+    def __init__(self, mode="base", bit=8, is_signed=True, is_enable=False, is_input=False, args=None, operator=None):
+        super().__init__()
+        self.mode = mode
+        self.is_input = is_input
+        self.is_signed = is_signed
+        self.is_enable = is_enable
+        self.is_enable_activation = is_enable
+        self.is_enable_weight = is_enable
+        self.args = args
+        self.operator = operator
+
+        self.alpha = nn.Parameter(torch.tensor(1.0, requires_grad=True))
+        self.register_buffer('bit', torch.tensor(bit))
+        self.register_buffer('has_inited_quant_para', torch.tensor(0.0))
+        self.register_buffer('quant_grid', torch.ones(2 ** bit))
+        if self.flavor == "olive":
+            self.register_buffer('outliers', torch.ones(2 ** bit))
+
+        self.w_up, self.a_up = self.args.w_up, self.args.a_up
+        self.w_low, self.a_low = self.args.w_low, self.args.a_low
+        self.percent = self.args.percent / 100
+        self.is_perchannel = not is_input            # inputs are never per-channel
+        self.search = args.search
+        self.mse = torch.tensor(0.0)
+        self.name = None
+
+        self._cb = None
+        self._cb_key = None
+        self._inited_key = None
+        self._inited_val = False
+
+    # ------------------------------------------------------------------ toggles
+    def disable_input_quantization(self):
+        self.is_enable_activation = False
+
+    def enable_quantization(self, name):
+        self.name = name
+        self.is_enable = True
+
+    def disable_quantization(self, name):
+        self.name = name
+        self.is_enable = False
+
+    def update_signed(self, tensor):
+        if tensor.min() < 0:
+            self.is_signed = True
+
+    # ---------------------------------------------------------------- codebooks
+    def _bits(self):
+        return int(self.bit.item())
+
+    def _no_outlier(self):
+        return self.flavor != "olive" or bool(getattr(self.args, "no_outlier", False))
+
+    def convert_tensor(self, values):
+        return codebooks._ant_finish(list(values), self._bits(), self.quant_grid.device)
+
+    def int_value(self, q_type="int"):
+        if self.flavor == "olive":
+            return codebooks.olive_grid("int", self._bits(), self.is_signed, self.quant_grid.device)
+        if q_type == "int":
+            return codebooks.ant_grid("int", self._bits(), self.is_signed, self.quant_grid.device)
+        B = codebooks._vbits(self._bits(), self.is_signed)
+        return self.convert_tensor(codebooks._mirror(codebooks.int_magnitudes(B), self.is_signed))
+
+    def flint_value(self, exp_base=0):
+        if self.flavor == "olive":
+            return codebooks.olive_grid("flint", self._bits(), self.is_signed, self.quant_grid.device)
+        g = codebooks.ant_grid("flint", self._bits(), self.is_signed, self.quant_grid.device)
+        return g          # exp_base only shifts the table before it is renormalised to max = 10
+
+    def pot_value(self):
+        return codebooks.ant_grid("pot", self._bits(), self.is_signed, self.quant_grid.device)
+
+    def float_value(self, eb=3):
+        return codebooks.ant_grid("float%d" % eb, self._bits(), self.is_signed, self.quant_grid.device)
+
+    def apot_value(self):
+        return codebooks.ant_grid("apot", self._bits(), self.is_signed, self.quant_grid.device)
+
+    def outlier_value(self, exp_bit=2, exp_base=5):
+        return codebooks.olive_outliers(self._bits(), self.is_signed, exp_bit, exp_base, self.quant_grid.device)
+
+    def _grid_for(self, kind):
+        if self.flavor == "olive":
+            if kind in ("int", "flint"):
+                return codebooks.olive_grid(kind, self._bits(), self.is_signed, self.quant_grid.device)
+            raise RuntimeError("Unsupported mode: " + kind)
+        return codebooks.ant_grid(kind, self._bits(), self.is_signed, self.quant_grid.device)
+
+    def _grid_max(self):
+        return torch.max(self.quant_grid)
+
+    def _codebook(self, device):
+        """Prepared device codebook, rebuilt only when the grid buffers change
+        (load_state_dict / load_ant_state_dict / type search assign new tensors)."""
+        g = self.quant_grid
+        o = None if self._no_outlier() else self.outliers
+        key = (g.data_ptr(), g._version, g.numel(), str(device),
+               None if o is None else (o.data_ptr(), o._version, o.numel()))
+        if key != self._cb_key:
+            self._cb = ops.prepare_codebook(g.to(device), None if o is None else o.to(device))
+            self._cb_key = key
+        return self._cb
+
+    # ------------------------------------------------------------------ forward
+    def _launch(self, x, alpha):
+        if not x.is_cuda:
+            raise RuntimeError("antquant (B200): quantization needs CUDA tensors; there is no CPU fallback")
+        xc = x if x.is_contiguous() else x.contiguous()
+        cb = self._codebook(xc.device)
+        return ops.fakequant(xc, alpha, cb, self.is_perchannel, ovp=not self._no_outlier()).view(x.shape)
+
+    def _forward(self, data, display=False):
+        if self.flavor == "olive" or not torch.is_grad_enabled() or not (data.requires_grad or self.alpha.requires_grad):
+            with torch.no_grad():
+                return self._launch(data, self.alpha.detach())
+        return _FakeQuantSTE.apply(data, self.alpha, self)
+
+    # -------------------------------------------------------------- calibration
+    def mse_loss(self, quant_tensor, source_tensor, p=2.0, is_perchannel=True):
+        d = (quant_tensor - source_tensor).abs().pow(p)
+        if is_perchannel:
+            return d.view(quant_tensor.shape[0], -1).mean(-1).unsqueeze(1)
+        return d.mean()
+
+    def _base_alpha(self, tensor, per_row):
+        if self.flavor == "olive" and not self._no_outlier():        # 3-sigma clipping init (O/...:192-198,213-218)
+            if per_row:
+                v = tensor.reshape(tensor.shape[0], -1).float()
+                mean, std = v.mean(dim=-1), v.std(dim=-1)
+            else:
+                v = tensor.float()
+                mean, std = v.mean(), v.std()
+            return torch.maximum((mean + 3 * std).abs(), (mean - 3 * std).abs()).reshape(-1)
+        return ops.absmax(tensor, per_row)
+
+    def _candidates(self, per_row):
+        lb, ub = (int(self.w_low), int(self.w_up)) if per_row else (int(self.a_low), int(self.a_up))
+        if self.flavor == "ant":
+            if self.bit > 6:
+                lb = 95
+            return [i * 0.01 for i in range(lb, ub)]
+        return [i * 0.01 for i in range(lb, ub, 2)]
+
+    def search_mse(self, tensor):
+        """One fused sweep instead of the reference's Python loop: every candidate
+        alpha = base * (i * 0.01) is scored in a single pass over the tensor."""
+        per_row = self.is_perchannel and (not self.is_input)
+        x = tensor.detach()
+        x = x if x.is_contiguous() else x.contiguous()
+        base = self._base_alpha(x, per_row).float()
+        ratios = torch.tensor(self._candidates(per_row), dtype=torch.float32, device=x.device)
+        cb = self._codebook(x.device)
+        cols = x.numel() // base.numel()
+        ovp = not self._no_outlier()
+        if ovp and (x.numel() % 2 or (per_row and cols % 2)):
+            err = self._sweep_loop(x, base, ratios, per_row)          # pairs straddle rows / wrap around: rare shapes
+        else:
+            err = ops.mse_sweep(x, base, ratios, cb, per_row, ovp=ovp)                       # [n_cand, rows] sums
+        score = err / cols
+        best, idx = score.min(dim=0)                                   # first minimum, like the strict `<` update
+        first = (score == best.unsqueeze(0)).to(torch.int8).argmax(dim=0)
+        alpha = base * ratios[first]
+        if per_row:
+            alpha = alpha.unsqueeze(1)
+            x_max = base.unsqueeze(1)
+        else:
+            alpha = alpha.reshape(())
+            x_max = base.reshape(())
+        self.alpha.data = alpha.to(self.alpha.dtype)
+        return best.sum().float(), alpha, (alpha / x_max).mean().item()
+
+    def _sweep_loop(self, x, base, ratios, per_row):
+        """Candidate loop through the fused forward (shapes the sweep kernel declines)."""
+        errs = []
+        for r in ratios:
+            a = (base * r)
+            q = self._launch(x, a.unsqueeze(1) if per_row else a.reshape(()))
+            e = (q.double() - x.double()) ** 2
+            errs.append(e.reshape(base.numel(), -1).sum(1))
+        return torch.stack(errs)
+
+    def search_adaptive_numeric_type(self, data):
+        """One type per tensor: the candidate whose best summed MSE is smallest
+        (A/...:328-415; OliVe: int and flint only, O/...:236-256)."""
+        names, scores = [], []
+        mode = self.mode
+        order = ["int", "flint"] if self.flavor == "olive" else \
+            ["int", "flint", "pot", "float", "float1", "float2", "float3", "float4", "apot"]
+        for tok in order:
+            if ("-" + tok) not in mode:
+                continue
+            # reference quirk kept: the -float2/3/4 probes all score float_value(1) (A/...:379,388,397)
+            kind = "float1" if tok in ("float2", "float3", "float4") else tok
+            self.mode = tok
+            self.quant_grid.data = self._grid_for(kind)
+            s, _, _ = self.search_mse(data)
+            names.append(tok)
+            scores.append(s.item())
+        self.mode = names[int(np.argsort(np.array(scores))[0])]
+
+    def outlier_set(self, data):
+        """OLAccel-style baseline (mode == 'outlier', A/...:417-436)."""
+        def reduce_ave(t):
+            rt = t.clone()
+            if _dist_on():
+                dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+                rt /= dist.get_world_size()
+            return rt
+        self.percent_value_int4 = torch.tensor(np.percentile(data.abs().float().cpu().numpy(), self.percent * 100),
+                                               device=data.device, dtype=torch.float32)
+        self.percent_value_int16 = data.abs().max().float()
+        self.percent_value_int4.data = reduce_ave(self.percent_value_int4.data)
+        self.percent_value_int16.data = reduce_ave(self.percent_value_int16.data)
+        if _rank0():
+            print(self.name, self.percent_value_int4.item(), self.percent_value_int16.item())
+        self.is_perchannel = False
+        self.quant_grid.data = self.int_value()
+        self.has_inited_quant_para.data = torch.ones_like(self.has_inited_quant_para)
+
+    def outlier_quant(self, data):
+        """A/...:438-465."""
+        mask_int16 = data.abs() > self.percent_value_int4
+        if self.percent_value_int4 > 0:
+            tensor = self._launch(data.detach(), self.percent_value_int4.reshape(())).clone()
+        else:
+            tensor = data.clone().detach()
+        level = 2 ** 16 - 1 if self.is_signed else 2 ** 15 - 1
+        if self.percent < 100:
+            scale = (self.percent_value_int16 - self.percent_value_int4) / level
+            big = data[mask_int16]
+            q = ((big.abs() - self.percent_value_int4) / scale).round() * scale + self.percent_value_int4
+            q = q * big.sign()
+            tensor[mask_int16] = (q - tensor[mask_int16]).detach() + tensor[mask_int16]
+        return tensor
+
+    def _is_inited(self):
+        """`has_inited_quant_para == 0` without a host sync on every call: the buffer is re-read
+        only when it was reassigned (load_state_dict, set_8_bit_layer_*)."""
+        b = self.has_inited_quant_para
+        key = (b.data_ptr(), b._version)
+        if key != self._inited_key:
+            self._inited_val = bool(b.item() != 0)
+            self._inited_key = key
+        return self._inited_val
+
+    def _init_quant_para(self, data, data_b=None):
+        with torch.no_grad():
+            if self._is_inited():
+                return
+            self.update_signed(data)
+            if self.flavor == "olive":
+                self.outliers.data = self.outlier_value().to(self.outliers.device)
+            per_row = self.is_perchannel
+            a0 = ops.absmax(data.detach().contiguous(), per_row)
+            self.alpha.data = a0.unsqueeze(1) if per_row else a0.reshape(())
+
+            if self.flavor == "ant" and self.mode == 'outlier':
+                return self.outlier_set(data)
+
+            if self.bit > 6:
+                self.mode = 'int'
+            elif "ant-" in self.mode:
+                self.search_adaptive_numeric_type(data)
+
+            valid = ("int", "flint") if self.flavor == "olive" else \
+                ("int", "flint", "pot", "apot", "float", "float1", "float2", "float3", "float4")
+            if self.mode not in valid:
+                raise RuntimeError("Unsupported mode: " + self.mode)
+            self.quant_grid.data = self._grid_for(self.mode)
+
+            _, alpha, _ = self.search_mse(data)
+            self.alpha.data = alpha.to(self.alpha.dtype)
+
+            quant_data = self._forward(data)
+            self.mse = self.mse_loss(quant_data.float(), data.float(), 2, is_perchannel=self.is_perchannel).mean()
+            if self.flavor == "ant" and _dist_on():
+                dist.broadcast(self.mse, 0)
+            if _rank0() or self.flavor == "olive":
+                print(self.mode, end="\t")
+                print("%d-bit \t %s," % (self.bit.item(), self.name))
+            self._sync_after_calibration()
+            self.has_inited_quant_para.data = torch.ones_like(self.has_inited_quant_para)
+
+    def _sync_after_calibration(self):
+        """The only exchange step of the path, once per quantizer: the calibrated scale is averaged
+        over the data-parallel ranks and rank 0's type choice (its grid) wins (A/...:517-531).
+        No-op without a process group and for OliVe (whose reference never calls torch.distributed)."""
+        if self.flavor != "ant" or not _dist_on():
+            return
+        rt = self.alpha.data.clone()
+        dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+        self.alpha.data = rt / dist.get_world_size()
+        dist.broadcast(self.quant_grid, 0)
+
+    def tensor_forward(self, tensor, input_tensor=None):
+        if self.mode == "base" or not self.is_enable:
+            return tensor
+        if self.is_input:
+            if not self.is_enable_activation:
+                return tensor
+        elif not self.is_enable_weight:
+            return tensor
+        with torch.no_grad():
+            self._init_quant_para(tensor, input_tensor)
+        if self.flavor == "ant" and self.mode == 'outlier':
+            return self.outlier_quant(tensor)
+        return self._forward(tensor)
+
+
+class TensorQuantizer(Quantizer):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+    def forward(self, tensor, input_tensor=None):
+        return self.tensor_forward(tensor, input_tensor)
+
+
+class OliveQuantizer(Quantizer):
+    flavor = "olive"
+
+    @torch.no_grad()
+    def tensor_forward(self, tensor, input_tensor=None):
+        return super().tensor_forward(tensor, input_tensor)
+
+
+class OliveTensorQuantizer(OliveQuantizer):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+    def forward(self, tensor, input_tensor=None):
+        return self.tensor_forward(tensor, input_tensor)
