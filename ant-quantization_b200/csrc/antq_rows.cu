@@ -40,7 +40,10 @@ namespace {
 #define ANTQ_LOOP_VECS 2      // vectors per lane per loop iteration
 #endif
 constexpr int kWarpsPerCta = 4;
-constexpr int kCtasPerSm = 3;
+#ifndef ANTQ_CTAS
+#define ANTQ_CTAS 3
+#endif
+constexpr int kCtasPerSm = ANTQ_CTAS;
 constexpr int kNumSms = 148;
 #ifndef ANTQ_RING
 #define ANTQ_RING 2      // measured best on 4096x4096 fp16 (profiles/r01_tuning.md): deeper rings front-load the
@@ -490,11 +493,11 @@ antq_rows_kernel(const RowsParams p) {
         }
         if (++iidx == p.chunks_per_row) { iidx = 0; ++irow; }
     };
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kRing - 1; k++)
-            if (c_begin + k < c_end) issue(k);
-    }
+    // Only the FIRST chunk is requested up front; the rest of the ring is filled once it has landed.
+    // Requesting ring-depth chunks from every warp at t = 0 puts most of a small tensor in the memory
+    // queue at once and delays every warp's first chunk (profiles/r01_tuning.md).
+    long long issued = c_begin;               // next chunk to issue (meaningful on lane 0)
+    if (lane == 0) { issue(0); issued = c_begin + 1; }
 
     // this lane's codebook entries stay in registers for the whole kernel
     const int nt_real = p.nt_real;
@@ -516,7 +519,10 @@ antq_rows_kernel(const RowsParams p) {
     for (long long c = c_begin; c < c_end; ++c) {
         const int slot = (int)((c - c_begin) & (kRing - 1));
         // keep the ring full: the slot freed by the previous iteration receives chunk c + kRing - 1
-        if (lane == 0 && c + (kRing - 1) < c_end) issue((slot + kRing - 1) & (kRing - 1));
+        if (lane == 0 && c != c_begin) {
+            const long long want = (c + kRing) < c_end ? (c + kRing) : c_end;
+            while (issued < want) { issue((int)((issued - c_begin) & (kRing - 1))); ++issued; }
+        }
 
         if (row != cur_row) {
             // ---- table rebuild for a new row (copies for this and the next chunks are already in flight) ----
@@ -611,6 +617,10 @@ antq_rows_kernel(const RowsParams p) {
         if (nvec > 0) {
             antq_mbar_wait(mbar + slot, (phases >> slot) & 1u);        // the chunk has landed in shared memory
             phases ^= 1u << slot;
+            if (lane == 0 && c == c_begin) {                             // first chunk is in: fill the ring
+                const long long want = (c + kRing) < c_end ? (c + kRing) : c_end;
+                while (issued < want) { issue((int)((issued - c_begin) & (kRing - 1))); ++issued; }
+            }
             const uint4 *sv = reinterpret_cast<const uint4 *>(wbase + slot * kChunkBytes);
             bool skipped = !row_ok;
             if (row_ok)

@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_modules.py -m gpu -q 2>&1 | tail -40
+timeout 900 python -m pytest tests/test_gpu_reference_kernel.py -m gpu -q 2>&1 | tail -8
+python tools/ref_gpu_bench.py 2>&1 | tail -2 | tee gpurun_out/ref_gpu_bench_r01.json
