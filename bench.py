@@ -28,7 +28,10 @@ N, NB = 4096, 8                 # tensor side, tensors per step
 BYTES_PER_ELEM = 4              # fp16 in + fp16 out
 WORKLOAD = "opt6.7b-attn-weight 4096x4096 fp16 -> flint-4 (signed, per-channel alpha) -> fp16, 8 tensors/step"
 METRIC = "quant-dequant GB/s (% HBM peak), 4096x4096 fp16->4b flint"
-NCU_TRAFFIC_BYTES = None        # dram read+write per launch from profiles/ (ncu --set full); None until captured
+# dram__bytes_read.sum (33.64 MB, profiles/r01_rows_kernel_ncu_summary.csv) + the 33.55 MB of stores; ncu's
+# dram__bytes_write.sum shows only 0.6-0.7 MB inside the kernel window because the stores are still dirty in the
+# 126 MB L2 when the kernel ends (profiles/r01_notes.md)
+NCU_TRAFFIC_BYTES = 33637888 + 33554432
 
 
 def hbm_peak():
@@ -294,7 +297,7 @@ def main():
                    "pct_of_hbm_peak": round(100.0 * value / world / peak, 2)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES,
-                     "kernel": "antq_rows_kernel<__half,7,SYM>", "launch_us": round(launch_us, 3),
+                     "kernel": "antq_rows_kernel<__half,7,SYM,noOVP,nocodes>", "launch_us": round(launch_us, 3),
                      "algorithmic_bytes_per_launch": N * N * BYTES_PER_ELEM, "peak_source": peak_src},
         "e2e": e2e, "gpu_launches": args.steps * NB, "clocks": clocks,
     }

@@ -166,3 +166,25 @@ RESULT["mha_modes"] = sorted(set(m.mode for m in qm.modules() if isinstance(m, T
     assert res["mha_type"] == "MultiheadAttentionQuantizer" and res["mha_err"] < 1e-5
     assert res["mha_q_shape"] == [3, 7, 32] and res["mha_w_shape"] == [3, 7, 7] and res["mha_q_differs"]
     assert set(res["mha_modes"]) <= {"int", "flint"}
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The reference-side binding shown in INTEGRATION.md is real code: run it against the oracle."""
+    import re
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import antq_oracle as orc
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = [b for b in re.findall(r"```python\n(.*?)```", md, re.S) if "antq_codebook_prepare" in b][0]
+    block = block.replace("/path/to/repo", ROOT)
+    ns = {}
+    exec(block, ns)
+    dev = torch.device("cuda:0")
+    grid = orc.ant_grid("flint", 4, True)
+    x = (torch.randn(64, 1024) * 0.02).to(torch.float16)
+    alpha = x.float().abs().amax(1) * 0.9
+    cb, info = ns["prepare"](torch.from_numpy(grid).to(dev))
+    y = ns["fake_quant"](x.to(dev), alpha.to(dev), cb, info, True)
+    ref = orc.ant_forward(x.numpy(), alpha.numpy(), grid, per_row=True)
+    assert np.array_equal(y.cpu().numpy().view(np.uint16), ref.view(np.uint16))
