@@ -101,12 +101,18 @@ def make_inputs(torch, device, nb, seed):
     return xs, alphas
 
 
+def _all_host_threads(orc):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    return orc.set_threads(os.cpu_count() or 1)
+
+
 def cpu_reference_leg(seconds_target=10.0, rows=None):
     """The reference path restated on the CPU (oracle/, 'port'): literal scan + fp32 arithmetic,
     OpenMP over rows.  Bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import antq_oracle as orc
+    cores = _all_host_threads(orc)
     rows = rows or N
     rng = np.random.default_rng(0)
     x = (rng.standard_normal((rows, N)) * 0.02).astype(np.float16)
@@ -122,7 +128,6 @@ def cpu_reference_leg(seconds_target=10.0, rows=None):
         if dt >= seconds_target or reps >= 400:
             break
     gbs = reps * rows * N * BYTES_PER_ELEM / dt / 1e9
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": "port",
             "sample": "%d x (%dx%d fp16 flint-4 per-channel), oracle/antq_oracle.c literal scan, OpenMP, %.1f s"
                       % (reps, rows, N, dt)}
@@ -135,6 +140,7 @@ def run_reference_arm(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import antq_oracle as orc
+    cores = _all_host_threads(orc)
     rows = 1024                                         # bounded sample: a quarter tensor per step
     rng = np.random.default_rng(0)
     x = (rng.standard_normal((rows, N)) * 0.02).astype(np.float16)
@@ -147,7 +153,6 @@ def run_reference_arm(args):
         orc.ant_forward(x, alpha, grid, per_row=True)
     dt = time.perf_counter() - t0
     gbs = args.steps * rows * N * BYTES_PER_ELEM / dt / 1e9
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     sample = "%d steps x (%dx%d fp16 flint-4 per-channel) on %d host threads" % (args.steps, rows, N, cores)
     line = {"impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),

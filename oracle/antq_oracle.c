@@ -201,4 +201,19 @@ void antq_oracle_ant_forward_f16(const _Float16 *x, _Float16 *out, int32_t *code
     }
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline sets its thread count explicitly. */
+int antq_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int antq_oracle_abi_version(void) { return 1; }
