@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SUFFIX = os.environ.get("ANTQ_LIB_SUFFIX", "")
 OUT = os.path.join(CSRC, "libantq%s.so" % SUFFIX)
-SOURCES = ["antq_prepare.cu", "antq_rows.cu", "antq_flat.cu", "antq_capi.cu", "antq_debug.cu"]
+SOURCES = ["antq_prepare.cu", "antq_rows.cu", "antq_stream.cu", "antq_flat.cu", "antq_capi.cu", "antq_debug.cu"]
 HEADERS = ["antq_common.cuh", os.path.join("..", "..", "include", "antq.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -45,7 +45,7 @@ def _compile(src):
 def build(force=False, verbose=False):
     if not (force or _stale()):
         return OUT
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(_compile, SOURCES))
     cmd = [NVCC, "-shared", "--cudart=static", "-o", OUT] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -2,6 +2,7 @@
 // checks, kernel selection, and the host-buffer pipeline.  No torch, no C++
 // types across the boundary, no allocation/synchronisation in device entry points.
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 
 #include "antq_common.cuh"
@@ -9,6 +10,8 @@
 int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp,
                      cudaStream_t st);
+int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                       int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
 int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
 int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
@@ -26,7 +29,7 @@ extern "C" {
 int antq_abi_version(void) { return ANTQ_ABI_VERSION; }
 
 const char *antq_build_info(void) {
-    return "libantq sm_100a; kernels: antq_prepare_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
+    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
            "antq_mse_sweep_kernel; built " __DATE__;
 }
 
@@ -93,6 +96,14 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
     if (plan < 0) return plan;
     const AntqCodebook *cb = (const AntqCodebook *)codebook;
     if (plan == 1) {
+        // hot path: the persistent producer/consumer kernel; the per-warp row kernel keeps the code-emitting variant
+        static int use_rows = -1;
+        if (use_rows < 0) { const char *e = getenv("ANTQ_KERNEL"); use_rows = (e && !strcmp(e, "rows")) ? 1 : 0; }
+        if (!codes && !use_rows) {
+            const int rc = antq_launch_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
+                                              (cudaStream_t)stream);
+            if (rc != ANTQ_ENOTSUP) return rc;
+        }
         return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
                                 (cudaStream_t)stream);
     }

@@ -1,0 +1,795 @@
+// antq_stream.cu -- the hot kernel: fused fake-quant forward, one persistent CTA per SM.
+//
+// Replaces A/antquant/quant_modules.py:535-551 (+ O/...:295-330 with OVP) and the scan kernel it
+// calls (A/quant/quant_kernel.cu:11-39): ~9 launches and 7 reads + 7 writes of the tensor become
+// ONE launch, one read, one write.
+//
+// Arithmetic: identical to antq_rows.cu (x-space thresholds, exact STE window; proved bit-exact on
+// exhaustive fp16 inputs in tests/test_xspace_model.py).  Per 32-bit register (two 16-bit values):
+//   ALU-pipe chain   m = HSET2.BM(|x| >= X_i);  q ^= m & E_i          (E_i = O_{i+1} xor O_i)
+//   FMA-pipe chain   m = HFMA2.SAT(|x|S, B_i, C_i);  q = HFMA2(m, D_i, q)   (exact, see build_tables)
+// and the pairs of every vector are split between the two chains because both pipes are half-rate.
+//
+// Execution shape (B200): 148 CTAs, one per SM, each owning an equal contiguous range of chunks
+// (<= 8 KiB pieces that never straddle a row).  Warp 0 is the PRODUCER: it walks the range, puts
+// every chunk in flight with one TMA bulk copy (cp.async.bulk -> shared memory, completion on the
+// stage's `full` mbarrier) as soon as the stage's `empty` mbarrier allows, and -- while the bytes are
+// in flight -- builds the row's tables (thresholds, outputs, FMA twins), lane-parallel over the
+// thresholds of up to 32/(NT+1) rows at once, and publishes them next to the data in the same stage.
+// The other warps are CONSUMERS: they take the next chunk number from a shared counter, wait for its
+// stage, pull the tables into registers, run the chains from shared memory straight to global
+// memory (LDS.128 -> STG.128), and release the stage.  No CTA-wide barrier after start-up.
+//
+// Out-of-window values (|d| > lim, NaN, Inf) are detected with one running packed max per register;
+// the chunk is still in shared memory when the test fires, so a cold pass recomputes exactly those
+// vectors with the literal reference arithmetic (also in place).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "antq_common.cuh"
+
+namespace {
+
+#ifndef ANTQS_CONSUMERS
+#define ANTQS_CONSUMERS 12
+#endif
+#ifndef ANTQS_BUILDERS
+#define ANTQS_BUILDERS 3
+#endif
+#ifndef ANTQS_STAGES
+#define ANTQS_STAGES 24
+#endif
+#ifndef ANTQS_CHUNK
+#define ANTQS_CHUNK 8192
+#endif
+constexpr int kNC = ANTQS_CONSUMERS;      // consumer warps per CTA
+constexpr int kNS = ANTQS_STAGES;         // ring stages per CTA
+constexpr int kChunkMax = ANTQS_CHUNK;    // bytes of tensor per stage
+constexpr int kNumSms = 148;
+constexpr int kMetaWords = 8;
+constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
+constexpr int kThreads = (kNC + 1 + kNB) * 32;   // consumers | issuer | builders
+constexpr int kRT = 32;                    // row-table ring slots (power of two)
+static_assert(kNS - 1 + 8 <= kRT, "a consumer can be kNS - 1 rows ahead of the slowest one; G <= 8 rows per build");
+static_assert(kNS % kNC == 0, "every consumer meets its stages in lap order");
+
+enum : uint32_t { kRowOk = 1u, kRowTies = 2u, kRowFma = 4u };
+
+template <int NT> struct TabGeom {
+    static constexpr int NTP = NT + 1;                 // table pitch in words: 4, 8, 16, 32
+    static constexpr int G = 32 / NTP;                 // rows built at once by the producer warp
+    static constexpr int kTabBytes = ((6 * NTP + kMetaWords) * 4 + 127) / 128 * 128;
+};
+
+struct StreamParams {
+    const void *x;
+    void *out;
+    const float *alpha;
+    const AntqCodebook *cb;
+    long long rows, cols;
+    unsigned total_chunks, chunks_per_cta, chunks_rem;   // CTA b owns chunks_per_cta (+1 if b < chunks_rem) chunks
+    int alpha_per_row, chunks_per_row, chunk_elems;
+    int nt_real, mid, ovp_index, n_entries;
+    float gmax, lim;
+    int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin
+    int stages;         // ring stages in use (<= kNS, multiple of kNP); ANTQ_STAGES experiments
+    unsigned long long *trace;   // ANTQS_TRACE builds: per-CTA timeline (tools/trace_stream.py)
+};
+
+#ifdef ANTQS_TRACE
+constexpr int kTraceChunks = 64, kTraceStride = 8 + 4 * kTraceChunks;
+__device__ __forceinline__ unsigned long long antqs_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define ANTQS_TR(slot) do { if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * kTraceStride + (slot)] = antqs_now(); } while (0)
+#define ANTQS_TRK(k, what) do { if ((k) < kTraceChunks) ANTQS_TR(8 + 4 * (k) + (what)); } while (0)
+#else
+#define ANTQS_TR(slot) do { } while (0)
+#define ANTQS_TRK(k, what) do { } while (0)
+#endif
+
+// ---- mbarrier helpers not in antq_common.cuh ------------------------------------------------
+__device__ __forceinline__ void antqs_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
+}
+
+// ---- the literal reference arithmetic for the rare vectors the chains may not handle ---------
+template <typename T, bool OVP>
+__device__ __noinline__ void antqs_slow_vec(const AntqCodebook *__restrict__ cb, float s, const T *xv, T *og, int n) {
+    typedef AntqType<T> A;
+    float q[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        if (e < n) {
+            AntqExact ex = antq_exact_quant(cb, A::to_f32(xv[e]), s);
+            q[e] = ex.q; d[e] = ex.d;
+        }
+    }
+    if (OVP) {
+#pragma unroll
+        for (int e = 0; e + 1 < 8; e += 2) {
+            if (e + 1 < n) {
+                const bool oe = fabsf(q[e]) > 32.0f, oo = fabsf(q[e + 1]) > 32.0f;
+                if (oe) q[e + 1] = __fmul_rn(q[e + 1], 0.0f);
+                else if (oo) q[e] = __fmul_rn(q[e], 0.0f);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        if (e < n) og[e] = A::from_f32_rn(antq_ste_rescale(q[e], d[e], s));
+}
+
+// Cold pass over a chunk still resident in shared memory: every vector holding an out-of-window
+// element (or every vector, when the row's scale is not a positive finite number) is recomputed.
+template <typename T, bool OVP>
+__device__ __noinline__ void antqs_fixup_chunk(const AntqCodebook *__restrict__ cb, float s, float xlim, bool all,
+                                               const uint4 *sv, T *og, int nvec, int lane) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    for (int v = lane; v < nvec; v += 32) {
+        const T *xv = reinterpret_cast<const T *>(sv + v);
+        bool special = all;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) special |= !(fabsf(A::to_f32(xv[e])) <= xlim);
+        if (special) antqs_slow_vec<T, OVP>(cb, s, xv, og + (long long)v * VEC, VEC);
+    }
+}
+
+// Exact (X, Xn) for a 16-bit type when the division-free shortcut could not prove them
+// (p = t*s within 16 fp32-ulps of a representable value): at most three divisions.
+template <typename T>
+__device__ __noinline__ void antqs_x_threshold16_near(float tpos, float tneg, float s, T *xp, T *xn) {
+    typedef AntqType<T> A;
+    T c = A::from_f32_rn(__fmul_rn(tpos, s));
+    float qc = __fdiv_rn(A::to_f32(c), s);
+    if (qc >= tpos) {
+        const T p = antq_next_down(c);
+        const float qp = __fdiv_rn(A::to_f32(p), s);
+        if (!antq_is_inf(p) && qp >= tpos) { c = p; qc = qp; }
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < 6 && !(qc >= tpos); ++it) {
+            c = antq_next_up(c);
+            qc = __fdiv_rn(A::to_f32(c), s);
+        }
+    }
+    *xp = c;
+    // the next 16-bit value is thousands of fp32-ulps further, tneg only a few: one test decides
+    *xn = (qc >= tneg) ? c : antq_next_up(c);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t antqs_word(T v) {
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t b = AntqType<T>::bits(v);
+        return b | (b << 16);
+    } else {
+        return __float_as_uint(v);
+    }
+}
+
+template <typename T> struct Pack2 {
+    typedef float2 v2;
+    __device__ static __forceinline__ v2 from_u32(uint32_t) { return make_float2(0.f, 0.f); }
+};
+template <> struct Pack2<__half> {
+    typedef __half2 v2;
+    __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
+    static constexpr uint32_t kOne = 0x3c003c00u;
+};
+template <> struct Pack2<__nv_bfloat16> {
+    typedef __nv_bfloat162 v2;
+    __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
+    static constexpr uint32_t kOne = 0x3f803f80u;
+};
+template <typename V> __device__ __forceinline__ uint32_t antqs_u32(const V &v) {
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+// ==================================================================================================
+// Producer side: the tables of one row, one lane per threshold.
+// ==================================================================================================
+struct RowTab {
+    uint32_t X, Xn, T2, B, C, D;            // this lane's entry of each table
+    uint32_t s_bits, flags, xlim, S2, xovp, xovpn;   // uniform over the lanes of one row group
+};
+
+//   X[i]   min{x in T : fl32(x / s) >= thr_i}   (x >= 0, or every x for an asymmetric codebook)
+//   Xn[i]  the same on |x| for x < 0: differs from X only where a tie x / s == midpoint is representable
+//          (ties go to the LATER grid entry: up for positive d, toward zero for negative d)
+//   T2     16-bit types: E[i] = O[i+1] ^ O[i] (+ a sign marker in E[0] for symmetric codebooks), and O[0] in
+//          slot NT;  fp32: O[i] = fl32(level_i * s), i <= NT
+//   B, C, D, S2   FMA-pipe twin (16-bit types, tie-free rows): with P = prev(X), u = X - P (a power of two),
+//          m = sat((S|x|) * (1/(uS)) - P/u) is exactly 1.0 for |x| >= X and exactly 0.0 for |x| <= P, because the
+//          fused product-sum is <= 0 or >= 1 before its single rounding; D[i] = O[i+1] - O[i] must be exactly
+//          representable (checked), so q <- m*D + q reproduces O[rank] without rounding.
+template <typename T, int NT, bool SYM, bool OVP>
+__device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, float alpha, float tpos, float tneg,
+                                             float lev, int sub, int grp, bool tr) {
+    typedef AntqType<T> A;
+    typedef TabGeom<NT> TG;
+    constexpr int NTP = TG::NTP;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int nt_real = p.nt_real;
+    const float inf = __int_as_float(0x7f800000);
+    const unsigned gmask = NTP == 32 ? kFull : (((1u << (NTP & 31)) - 1u) << (grp * NTP));
+
+    const float s = __fdiv_rn(alpha, p.gmax);                          // scale = alpha / max(grid)
+    const bool row_ok = s > 0.0f && s < inf;
+#ifdef ANTQS_TRACE
+    const int lane = sub + grp * NTP;
+    if (tr && row_ok) ANTQS_TR(5);
+#endif
+    T Xl = A::from_bits(A::kInf), Xnl = A::from_bits(A::kInf), Ol = A::from_bits(0);
+    if (row_ok) {
+        if (sub < nt_real) {
+            bool near;
+            Xl = antq_x_threshold<T>(tpos, s, &near);
+            Xnl = Xl;
+            if (SYM && near) {
+                // a negative input can land on the other side of a representable tie
+                if constexpr (sizeof(T) == 2) antqs_x_threshold16_near<T>(tpos, tneg, s, &Xl, &Xnl);
+                else Xnl = antq_x_threshold_exact<T>(tneg, s);
+            }
+        }
+        if (sub <= nt_real) Ol = A::from_f32_rn(__fmul_rn(lev, s));
+    }
+    const bool ties = (__ballot_sync(kFull, A::bits(Xl) != A::bits(Xnl)) & gmask) != 0;
+#ifdef ANTQS_TRACE
+    if (tr) ANTQS_TR(6);
+#endif
+    t.X = antqs_word<T>(Xl);
+    t.Xn = antqs_word<T>(Xnl);
+    t.s_bits = __float_as_uint(s);
+    t.flags = (row_ok ? kRowOk : 0u) | (ties ? kRowTies : 0u);
+    const float xl = __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);    // conservative window in x-space
+    t.xlim = antqs_word<T>(A::from_f32_rz(xl));
+    t.S2 = 0; t.B = 0; t.C = 0; t.D = 0;
+    {
+        const int oi = p.ovp_index;
+        const bool has = OVP && oi >= 0 && oi < NT;
+        const uint32_t infw = antqs_word<T>(A::from_bits(A::kInf));
+        const uint32_t xo = __shfl_sync(kFull, t.X, has ? oi : 0, NTP);
+        const uint32_t xon = __shfl_sync(kFull, t.Xn, has ? oi : 0, NTP);
+        t.xovp = has ? xo : infw;
+        t.xovpn = has ? xon : infw;
+    }
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t ob = A::bits(Ol);
+        const uint32_t ob_next = __shfl_down_sync(kFull, ob, 1, NTP);
+        const uint32_t o0 = __shfl_sync(kFull, ob, 0, NTP);
+        uint32_t e = sub < nt_real ? (ob ^ ob_next) : 0u;
+        if (SYM && sub == 0) e |= 0x8000u;                            // marker: "level is not the zero level"
+        if (sub == NT) e = o0;
+        t.T2 = e | (e << 16);
+
+        // FMA-pipe twin
+        bool ok = row_ok && !ties && NT <= 15 && !(p.debug & 16);
+        // S = 2^k with xlim * S in [2^13, 2^14): every in-window |x| stays finite after scaling
+        int k = 13 - (int)((__float_as_uint(xl) >> 23) & 0xff) + 127;
+        k = k > 15 ? 15 : (k < -14 ? -14 : k);
+        const float S = __uint_as_float((unsigned)(127 + k) << 23);
+        ok = ok && isfinite(A::to_f32(Ol));
+        float Bv = 0.0f, Cv = -1.0f;              // padding: m = sat(0 * xs - 1) = 0
+        if (sub < nt_real) {
+            const T P = antq_next_down(Xl);
+            if (antq_is_inf(Xl)) {
+                Bv = 0.0f; Cv = -1.0f;                                   // never reached
+            } else if (antq_is_inf(P)) {
+                Bv = 0.0f; Cv = 1.0f;                                    // always reached
+            } else {
+                const float u = __fsub_rn(A::to_f32(Xl), A::to_f32(P));  // exact power of two
+                const int eu = (int)((__float_as_uint(u) >> 23) & 0xff);       // u is a normal fp32
+                const float Bfull = __uint_as_float((unsigned)(254 - eu) << 23);                // 1 / u
+                const int eb = 254 - eu - k;
+                Bv = (eb >= 1 && eb <= 254) ? __uint_as_float((unsigned)eb << 23) : 0.0f;      // 1 / (u S)
+                Cv = -__fmul_rn(A::to_f32(P), Bfull);
+                ok = ok && Bv >= 6.103515625e-05f && Bv <= 32768.0f && fabsf(Cv) <= 2048.0f;
+                if (sizeof(T) == 2 && A::kInf == 0x7f80u) ok = ok && fabsf(Cv) <= 256.0f;  // bf16: 8-bit integers
+            }
+        }
+        // D_i = O[i+1] - O[i] must be exactly representable (fp32 difference of two 16-bit values is exact)
+        const float o_next = __shfl_down_sync(kFull, A::to_f32(Ol), 1, NTP);
+        const float dex = __fsub_rn(o_next, A::to_f32(Ol));
+        const T D = A::from_f32_rn(dex);
+        if (sub < nt_real) ok = ok && (A::to_f32(D) == dex);
+        const bool fma_ok = (__ballot_sync(kFull, ok) & gmask) == gmask;
+        t.D = antqs_word<T>(sub < nt_real ? D : A::from_bits(0));
+        t.B = antqs_word<T>(A::from_f32_rn(Bv));
+        t.C = antqs_word<T>(A::from_f32_rn(Cv));
+        t.S2 = antqs_word<T>(A::from_f32_rn(S));
+        if (fma_ok) t.flags |= kRowFma;
+    } else {
+        t.T2 = __float_as_uint(Ol);
+    }
+}
+
+// ==================================================================================================
+// Consumer side
+// ==================================================================================================
+template <int N> __device__ __forceinline__ void load_words(uint32_t (&dst)[N], const uint32_t *src) {
+    constexpr int NV = (N + 3) / 4;
+    uint4 b[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) b[i] = reinterpret_cast<const uint4 *>(src)[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint4 a = b[i / 4];
+        dst[i] = (i % 4 == 0) ? a.x : (i % 4 == 1) ? a.y : (i % 4 == 2) ? a.z : a.w;
+    }
+}
+
+enum { kModeAlu = 0, kModeTies = 1, kModeMix = 2 };
+
+// 16-bit element types: one 32-bit register = two elements (low half = even flat index).
+template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
+    typedef typename Pack2<T>::v2 v2;
+    static constexpr int NTP = NT + 1;
+    uint32_t X[NT + 1];                       // [NT] unused
+    uint32_t E[NT + 1];                       // [NT] = O[0]
+    uint32_t Xn[MODE == kModeTies ? NT + 1 : 1];
+    uint32_t Bf[MODE == kModeMix ? NT + 1 : 1], Cf[MODE == kModeMix ? NT + 1 : 1], Df[MODE == kModeMix ? NT + 1 : 1];
+    uint32_t S2, xovp, xovpn;
+    v2 mx;                                    // running max of |x| (NaN-propagating)
+
+    __device__ __forceinline__ void load(const uint32_t *tab, uint32_t s2, uint32_t xo, uint32_t xon) {
+        load_words<NT + 1>(X, tab);
+        load_words<NT + 1>(E, tab + 2 * NTP);
+        if constexpr (MODE == kModeTies) load_words<NT + 1>(Xn, tab + NTP);
+        if constexpr (MODE == kModeMix) {
+            load_words<NT + 1>(Bf, tab + 3 * NTP);
+            load_words<NT + 1>(Cf, tab + 4 * NTP);
+            load_words<NT + 1>(Df, tab + 5 * NTP);
+        }
+        S2 = s2; xovp = xo; xovpn = xon;
+        mx = Pack2<T>::from_u32(0u);
+    }
+
+    __device__ __forceinline__ uint32_t ovp_mask(v2 a2, uint32_t neg) const {
+        const uint32_t t = (SYM && MODE == kModeTies) ? ((neg & xovpn) | (~neg & xovp)) : xovp;
+        const uint32_t mo = __hge2_mask(a2, Pack2<T>::from_u32(t));      // element is an outlier
+        const uint32_t sw = __byte_perm(mo, 0, 0x1032);                  // swap halves
+        return sw & ~(mo & 0x0000ffffu);   // odd dies if even is outlier; even dies if only odd is
+    }
+
+    // ALU pipe: HSET2 + LOP3 per threshold
+    __device__ __forceinline__ uint32_t pair_alu(uint32_t xb) {
+        const v2 x2 = Pack2<T>::from_u32(xb);
+        const v2 ab = __habs2(x2);
+        const v2 a2 = SYM ? ab : x2;
+        mx = __hmax2_nan(mx, ab);
+        uint32_t neg = 0;
+        if (SYM && MODE == kModeTies) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));   // 0xffff where x < 0
+        uint32_t q = SYM ? 0u : E[NT];
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            uint32_t t = X[i];
+            if constexpr (SYM && MODE == kModeTies) t = (neg & Xn[i]) | (~neg & X[i]);
+            const uint32_t m = __hge2_mask(a2, Pack2<T>::from_u32(t));
+            q ^= m & E[i];
+        }
+        if (SYM) q &= xb | 0x7fff7fffu;        // keep the marker bit (level != 0) only where x is negative
+        if (OVP) q &= ~ovp_mask(a2, neg);
+        return q;
+    }
+
+    // FMA pipe: saturating-FMA compare + exact accumulate (tie-free rows only)
+    __device__ __forceinline__ uint32_t pair_fma(uint32_t xb) {
+        const v2 x2 = Pack2<T>::from_u32(xb);
+        const v2 ab = __habs2(x2);
+        mx = __hmax2_nan(mx, ab);
+        const v2 xs = __hmul2(SYM ? ab : x2, Pack2<T>::from_u32(S2));
+        v2 q = Pack2<T>::from_u32(E[NT]);
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            const v2 m = __hfma2_sat(xs, Pack2<T>::from_u32(Bf[i]), Pack2<T>::from_u32(Cf[i]));
+            q = __hfma2(m, Pack2<T>::from_u32(Df[i]), q);
+        }
+        uint32_t qb;
+        if (SYM) {
+            // (+-1) * q + 0: restores the sign and leaves a zero level at +0
+            const v2 sg = Pack2<T>::from_u32((xb & 0x80008000u) | Pack2<T>::kOne);
+            qb = antqs_u32(__hfma2(q, sg, Pack2<T>::from_u32(0u)));
+        } else {
+            qb = antqs_u32(q);
+        }
+        if (OVP) qb &= ~ovp_mask(SYM ? ab : x2, 0u);
+        return qb;
+    }
+
+    __device__ __forceinline__ uint4 vec(const uint4 r, int debug) {
+        if (debug & 2) return r;
+        uint4 q;
+        q.x = pair_alu(r.x);
+        q.z = pair_alu(r.z);
+        if constexpr (MODE == kModeMix) {
+            q.y = pair_fma(r.y);
+            q.w = pair_fma(r.w);
+        } else {
+            q.y = pair_alu(r.y);
+            q.w = pair_alu(r.w);
+        }
+        return q;
+    }
+    // true when some element this lane saw was NaN / Inf / outside the exact window
+    __device__ __forceinline__ bool special(uint32_t xlim) const {
+        return __hle2_mask(mx, Pack2<T>::from_u32(xlim)) != 0xffffffffu;
+    }
+};
+
+// fp32: one element per register; fp32 x-space resolves ties, so negatives always use Xn.
+template <int NT, bool SYM, bool OVP> struct Chain32 {
+    static constexpr int NTP = NT + 1;
+    uint32_t X[NT + 1], Xn[SYM ? NT + 1 : 1], O[NT + 1];
+    uint32_t xovp, xovpn;
+    float mx;
+
+    __device__ __forceinline__ void load(const uint32_t *tab, uint32_t, uint32_t xo, uint32_t xon) {
+        load_words<NT + 1>(X, tab);
+        if constexpr (SYM) load_words<NT + 1>(Xn, tab + NTP);
+        load_words<NT + 1>(O, tab + 2 * NTP);
+        xovp = xo; xovpn = xon;
+        mx = 0.0f;
+    }
+    __device__ __forceinline__ float one(float x, bool &outlier) {
+        const float ax = fabsf(x);
+        const float a = SYM ? ax : x;
+        const bool neg = SYM && (__float_as_int(x) < 0);
+        asm("max.NaN.f32 %0, %0, %1;" : "+f"(mx) : "f"(ax));          // NaN-propagating running max
+        float q = __uint_as_float(O[0]);
+        bool m0 = false;
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            bool m;
+            if constexpr (SYM) m = a >= __uint_as_float(neg ? Xn[i] : X[i]);
+            else m = a >= __uint_as_float(X[i]);
+            if (i == 0) m0 = m;
+            q = m ? __uint_as_float(O[i + 1]) : q;
+        }
+        if (SYM && m0) q = __uint_as_float(__float_as_uint(q) | (__float_as_uint(x) & 0x80000000u));
+        if (OVP) {
+            if constexpr (SYM) outlier = a >= __uint_as_float(neg ? xovpn : xovp);
+            else outlier = a >= __uint_as_float(xovp);
+        }
+        return q;
+    }
+    __device__ __forceinline__ uint4 vec(const uint4 r, int debug) {
+        if (debug & 2) return r;
+        const float xv[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
+        float qv[4];
+        bool ol[4] = {false, false, false, false};
+#pragma unroll
+        for (int k = 0; k < 4; k++) qv[k] = one(xv[k], ol[k]);
+        if (OVP) {
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                if (ol[k]) qv[k + 1] = 0.0f;
+                else if (ol[k + 1]) qv[k] = 0.0f;
+            }
+        }
+        return make_uint4(__float_as_uint(qv[0]), __float_as_uint(qv[1]), __float_as_uint(qv[2]),
+                          __float_as_uint(qv[3]));
+    }
+    __device__ __forceinline__ bool special(uint32_t xlim) const { return !(mx <= __uint_as_float(xlim)); }
+};
+
+// One chunk from shared memory to global memory: two vectors per lane per iteration, then the remainder.
+template <typename CH>
+__device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uint4 *sv, uint4 *og, int nvec, int lane,
+                                          uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim, int debug) {
+    ch.load(tab, s2, xo, xon);
+    const uint4 *sp = sv + lane;
+    uint4 *op = og + lane;
+    const int nfull = nvec >> 6;
+#pragma unroll 1
+    for (int it = 0; it < nfull; ++it) {
+        const uint4 r0 = sp[0], r1 = sp[32];                   // LDS.128, conflict free
+        const uint4 q0 = ch.vec(r0, debug);
+        const uint4 q1 = ch.vec(r1, debug);
+        antq_stg_stream(op, q0);
+        antq_stg_stream(op + 32, q1);
+        sp += 64; op += 64;
+    }
+#pragma unroll 1
+    for (int v = (nfull << 6) + lane; v < nvec; v += 32) {
+        const uint4 q0 = ch.vec(*sp, debug);
+        antq_stg_stream(op, q0);
+        sp += 32; op += 32;
+    }
+    return ch.special(xlim);
+}
+
+__device__ __forceinline__ unsigned antqs_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(antq_smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void antqs_st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(antq_smem_u32(p)), "r"(v) : "memory");
+}
+
+template <typename T, int NT, bool SYM, bool OVP>
+__global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamParams p) {
+    typedef AntqType<T> A;
+    typedef TabGeom<NT> TG;
+    constexpr int VEC = A::kVec;
+    constexpr int NTP = TG::NTP;
+    constexpr int G = TG::G;
+    constexpr int kTabBytes = TG::kTabBytes;
+    extern __shared__ __align__(128) unsigned char antqs_smem[];
+    unsigned char *ring = antqs_smem + (size_t)kNS * kChunkMax;                // kRT row-table slots
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kRT * kTabBytes);
+    uint64_t *empty = full + kNS;
+    unsigned *built = reinterpret_cast<unsigned *>(empty + kNS);               // [kNB] row groups finished per builder
+    unsigned *cons_row = built + kNB;                                          // [kNC] CTA-local row each consumer is on
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // equal contiguous share of the chunk list (32-bit: the launcher refuses tensors of more than 2^31 chunks)
+    const unsigned c_begin = blockIdx.x * p.chunks_per_cta + min(blockIdx.x, p.chunks_rem);
+    const int n = (int)p.chunks_per_cta + (blockIdx.x < p.chunks_rem ? 1 : 0);
+    const unsigned cpr = (unsigned)p.chunks_per_row;
+    const unsigned row_begin = c_begin / cpr;
+    const AntqCodebook *__restrict__ cb = p.cb;
+
+    if (warp == 0) ANTQS_TR(0);
+    if (threadIdx.x < kNS) {
+        antq_mbar_init(full + threadIdx.x, 1);
+        antq_mbar_init(empty + threadIdx.x, 1);
+    }
+    if (threadIdx.x < kNB + kNC) built[threadIdx.x] = 0;                       // built[] and cons_row[] are contiguous
+    __syncthreads();
+    if (warp == 0) ANTQS_TR(1);
+
+    if (warp == kNC) {
+        // ------------------------------ issuer ------------------------------
+        // Walks this CTA's chunks in order; a chunk goes in flight (one TMA bulk copy) the moment its stage is free.
+        unsigned row = row_begin;
+        int idx = (int)(c_begin - row * cpr);
+        const T *src_row = reinterpret_cast<const T *>(p.x) + (long long)row * p.cols;
+        int stage = 0;
+        unsigned parity = 1;                                          // a fresh barrier passes a parity-1 wait
+        for (int k = 0; k < n; ++k) {
+            antq_mbar_wait(empty + stage, parity);
+            if (lane == 0) {
+                const long long col0 = (long long)idx * p.chunk_elems;
+                const long long remain = p.cols - col0;
+                const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+                const unsigned bytes = (unsigned)(n_el / VEC) * 16u;
+                // (no fence.proxy.async: the consumer's reads of this stage are ordered before this copy by its
+                //  release-arrive on `empty` and the acquire-wait above, as in every TMA load pipeline)
+                if (bytes) antq_bulk_g2s(antqs_smem + (size_t)stage * kChunkMax, src_row + col0, bytes, full + stage);
+                else antqs_mbar_arrive(full + stage);
+            }
+            ANTQS_TRK(k, 0);
+            if (++idx == (int)cpr) { idx = 0; src_row += p.cols; }
+            if (++stage == p.stages) { stage = 0; parity ^= 1u; }
+        }
+    } else if (warp > kNC) {
+        // ------------------------------ table builders ------------------------------
+        // Builder b makes the tables of row groups b, b + kNB, ... (G rows per pass, one lane per threshold) and
+        // stores them in the row-table ring; it runs ahead of the consumers by up to kRT rows.
+        const int b = warp - kNC - 1;
+        const int sub = lane % NTP, grp = lane / NTP;
+        const int nt_real = p.nt_real;
+        const float inf = __int_as_float(0x7f800000);
+        const unsigned last_row = (unsigned)(p.rows - 1);
+        const unsigned row_last = (c_begin + (unsigned)n - 1u) / cpr;
+        const int ngroups = p.alpha_per_row ? (int)((row_last - row_begin) / G + 1) : 1;
+        auto alpha_of = [&](int g) {
+            unsigned r = row_begin + (unsigned)(g * G + grp);
+            r = r > last_row ? last_row : r;
+            return __ldg(p.alpha + (p.alpha_per_row ? r : 0));
+        };
+        float alpha_next = alpha_of(b);                               // prefetched one pass ahead
+        const float tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
+        const float tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : tpos;
+        const float lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
+        unsigned done = 0;
+        for (int g = b; g < ngroups; g += kNB) {
+            const int r0 = g * G;                                     // first CTA-local row of the group
+            if (r0 + G > kRT) {
+                // the slot of row r is reused by row r + kRT: wait until every consumer has moved past row r0 + G - 1 - kRT
+                const unsigned need = (unsigned)(r0 + G - kRT);       // all consumers must be on a row >= need
+                for (;;) {
+                    unsigned v = lane < kNC ? antqs_ld_acquire(cons_row + lane) : 0xffffffffu;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    if (v >= need) break;
+                    __nanosleep(200);
+                }
+            }
+            const float alpha = alpha_next;
+            if (g + kNB < ngroups) alpha_next = alpha_of(g + kNB);
+            const bool tr = (b == 0 && g == 0);
+            if (tr) ANTQS_TR(3);
+            RowTab tab;
+            build_tables<T, NT, SYM, OVP>(tab, p, alpha, tpos, tneg, lev, sub, grp, tr);
+            uint32_t *st = reinterpret_cast<uint32_t *>(ring + (size_t)((r0 + grp) & (kRT - 1)) * kTabBytes);
+            st[sub] = tab.X;
+            st[NTP + sub] = tab.Xn;
+            st[2 * NTP + sub] = tab.T2;
+            st[3 * NTP + sub] = tab.B;
+            st[4 * NTP + sub] = tab.C;
+            st[5 * NTP + sub] = tab.D;
+            if (sub == 0) {
+                uint4 *m = reinterpret_cast<uint4 *>(st + 6 * NTP);
+                m[0] = make_uint4(tab.s_bits, tab.flags, tab.xlim, tab.S2);
+                m[1] = make_uint4(tab.xovp, tab.xovpn, 0u, 0u);
+            }
+            __syncwarp();
+            ++done;
+            if (lane == 0) antqs_st_release(built + b, done);          // release: the group's tables are visible
+            if (tr) ANTQS_TR(4);
+        }
+    } else {
+        // ------------------------------ consumers ------------------------------
+        // Consumer w owns chunks w, w + kNC, ...: with stages % kNC == 0 it meets every stage it uses in lap order, so
+        // a parity wait can never alias a phase two laps back (a shared work counter could run a lap ahead).
+        int stage = warp;
+        unsigned parity = 0;
+        for (int k = warp; k < n; k += kNC, stage += kNC) {
+            if (stage >= p.stages) { stage -= p.stages; parity ^= 1u; }
+            const unsigned c = c_begin + (unsigned)k;
+            const unsigned row = c / cpr;
+            const int idx = (int)(c - row * cpr);
+            const unsigned rl = p.alpha_per_row ? row - row_begin : 0u;        // CTA-local row = table index
+            if (lane == 0) antqs_st_release(cons_row + warp, rl);              // builders may recycle slots of rows < rl
+            {
+                const unsigned g = rl / G;
+                const unsigned *flag = built + (g % kNB);
+                const unsigned need = g / kNB + 1u;
+                while (antqs_ld_acquire(flag) < need) __nanosleep(100);         // only at start-up in practice
+            }
+            ANTQS_TRK(k, 1);
+            const uint32_t *tab = reinterpret_cast<const uint32_t *>(ring + (size_t)(rl & (kRT - 1)) * kTabBytes);
+            const uint4 m0 = reinterpret_cast<const uint4 *>(tab + 6 * NTP)[0];
+            const uint4 m1 = reinterpret_cast<const uint4 *>(tab + 6 * NTP)[1];
+            const float s = __uint_as_float(m0.x);
+            const uint32_t flags = m0.y, xlim = m0.z;
+            const long long col0 = (long long)idx * p.chunk_elems;
+            const long long remain = p.cols - col0;
+            const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+            const int nvec = n_el / VEC, tail = n_el - nvec * VEC;
+            const long long base = (long long)row * p.cols + col0;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(antqs_smem + (size_t)stage * kChunkMax);
+            T *og = reinterpret_cast<T *>(p.out) + base;
+            antq_mbar_wait(full + stage, parity);                      // the chunk has landed in shared memory
+            ANTQS_TRK(k, 2);
+            bool special = !(flags & kRowOk);
+            if (nvec > 0 && !special) {
+                uint4 *ov = reinterpret_cast<uint4 *>(og);
+                if constexpr (sizeof(T) == 2) {
+                    if (flags & kRowTies) {
+                        Chain16<T, NT, SYM, OVP, kModeTies> ch;
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    } else if (flags & kRowFma) {
+                        Chain16<T, NT, SYM, OVP, (NT <= 15 ? kModeMix : kModeAlu)> ch;
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    } else {
+                        Chain16<T, NT, SYM, OVP, kModeAlu> ch;
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    }
+                } else {
+                    Chain32<NT, SYM, OVP> ch;
+                    special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                }
+            }
+            if (nvec > 0 && __any_sync(0xffffffffu, special)) {
+                float xl;
+                if constexpr (sizeof(T) == 2) xl = A::to_f32(A::from_bits((typename A::bits_t)(xlim & 0xffffu)));
+                else xl = __uint_as_float(xlim);
+                antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, nvec, lane);
+            }
+            // ragged tail (only a per-tensor view can have one: rows == 1): straight from global memory
+            if (tail > 0 && lane == 0) {
+                const T *xg = reinterpret_cast<const T *>(p.x) + base + (long long)nvec * VEC;
+                antqs_slow_vec<T, OVP>(cb, s, xg, og + (long long)nvec * VEC, tail);
+            }
+            __syncwarp();                                              // every lane is done with this stage
+            if (lane == 0) antqs_mbar_arrive(empty + stage);
+            ANTQS_TRK(k, 3);
+        }
+        if (lane == 0) antqs_st_release(cons_row + warp, 0xffffffffu);  // done: never holds a table slot again
+#ifdef ANTQS_TRACE
+        if (p.trace && lane == 0) atomicMax(p.trace + (size_t)blockIdx.x * kTraceStride + 2, antqs_now());
+#endif
+    }
+}
+
+template <typename T, int NT, bool SYM, bool OVP> int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
+    auto kernel = antq_stream_kernel<T, NT, SYM, OVP>;
+    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + 2 * kNS * 8 + (kNB + kNC) * 4 + 16;
+    static bool configured = false;      // per instantiation; the attribute is idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    kernel<<<dim3((unsigned)ctas), dim3(kThreads), smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        fprintf(stderr, "antq: stream kernel launch failed: %s (grid %d, block %d, smem %d, chunks %u)\n",
+                cudaGetErrorString(e), ctas, kThreads, smem, p.total_chunks);
+    return (int)e;
+}
+
+template <typename T, bool SYM, bool OVP> int launch_nt(const StreamParams &p, int nt, int ctas, cudaStream_t st) {
+#ifdef ANTQS_DEV_ONLY_NT7
+    if (nt <= 7) return launch_kernel<T, 7, SYM, OVP>(p, ctas, st);
+    return ANTQ_ENOTSUP;
+#else
+    if (nt <= 3) return launch_kernel<T, 3, SYM, OVP>(p, ctas, st);
+    if (nt <= 7) return launch_kernel<T, 7, SYM, OVP>(p, ctas, st);
+    if (nt <= 15) return launch_kernel<T, 15, SYM, OVP>(p, ctas, st);
+    if (nt <= 31) return launch_kernel<T, 31, SYM, OVP>(p, ctas, st);
+    return ANTQ_ENOTSUP;
+#endif
+}
+
+template <typename T> int launch_t(const StreamParams &p, int nt, bool sym, bool ovp, int ctas, cudaStream_t st) {
+    if (sym) return ovp ? launch_nt<T, true, true>(p, nt, ctas, st) : launch_nt<T, true, false>(p, nt, ctas, st);
+    return ovp ? launch_nt<T, false, true>(p, nt, ctas, st) : launch_nt<T, false, false>(p, nt, ctas, st);
+}
+
+}  // namespace
+
+static unsigned long long *antqs_trace_buffer = nullptr;
+// Tuning builds (-DANTQS_TRACE) record a per-CTA timeline into this device buffer (148 x 264 u64); NULL = off.
+extern "C" void antq_debug_stream_trace(void *device_buffer) { antqs_trace_buffer = (unsigned long long *)device_buffer; }
+
+// Returns ANTQ_ENOTSUP for configurations this kernel does not cover (the caller falls back to antq_rows_kernel).
+int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                       int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st) {
+    const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
+    const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
+    static int dbg = -1, chunk_env = 0, stages_env = 0;
+    if (dbg < 0) {
+        const char *e = getenv("ANTQ_DEBUG");
+        const char *c = getenv("ANTQ_CHUNK");
+        const char *g = getenv("ANTQ_STAGES");
+        chunk_env = c ? atoi(c) : 0;
+        stages_env = g ? atoi(g) : 0;
+        dbg = e ? atoi(e) : 0;
+    }
+    StreamParams p;
+    p.x = x; p.out = out; p.alpha = alpha; p.cb = cb;
+    p.rows = rows; p.cols = cols;
+    // chunk size: the largest power of two <= kChunkMax that still gives every consumer warp of every SM a chunk
+    int chunk_bytes = kChunkMax;
+    if (chunk_env >= 512 && chunk_env <= kChunkMax && (chunk_env & (chunk_env - 1)) == 0) {
+        chunk_bytes = chunk_env;
+    } else {
+        const long long want = (long long)kNumSms * kNC * 2;
+        while (chunk_bytes > 1024) {
+            const long long ce = chunk_bytes / es;
+            if (rows * ((cols + ce - 1) / ce) >= want) break;
+            chunk_bytes >>= 1;
+        }
+    }
+    p.chunk_elems = chunk_bytes / es;
+    const long long cpr = (cols + p.chunk_elems - 1) / p.chunk_elems;
+    if (cpr > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    p.chunks_per_row = (int)cpr;
+    const long long total = rows * cpr;
+    if (total == 0) return 0;
+    if (total > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    p.total_chunks = (unsigned)total;
+    p.alpha_per_row = alpha_per_row;
+    p.nt_real = nt; p.mid = info->mid; p.ovp_index = info->ovp_index; p.n_entries = info->n_entries;
+    p.gmax = info->gmax; p.lim = info->lim;
+    p.debug = dbg;
+    p.stages = (stages_env >= kNC && stages_env <= kNS && stages_env % kNC == 0) ? stages_env : kNS;
+    p.trace = antqs_trace_buffer;
+    const int ctas = (int)(p.total_chunks < (unsigned)kNumSms ? p.total_chunks : (unsigned)kNumSms);
+    p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
+    p.chunks_rem = p.total_chunks % (unsigned)ctas;
+    switch (dtype) {
+        case ANTQ_F32: return launch_t<float>(p, nt, sym, ovp, ctas, st);
+        case ANTQ_F16: return launch_t<__half>(p, nt, sym, ovp, ctas, st);
+        case ANTQ_BF16: return launch_t<__nv_bfloat16>(p, nt, sym, ovp, ctas, st);
+    }
+    return ANTQ_EINVAL;
+}

@@ -102,6 +102,8 @@ def _run_ant(antq, x_np, alpha_np, grid_np, per_row, flags=0, want_codes=False):
     a = torch.from_numpy(np.ascontiguousarray(alpha_np, dtype=np.float32)).to(dev())
     r = antq.fakequant(x, a, cb, per_row, want_codes=want_codes, flags=flags)
     if want_codes:
+        # codes come from antq_rows_kernel; the same call without codes takes antq_stream_kernel: both are checked
+        assert_bit_equal(to_np(antq.fakequant(x, a, cb, per_row, flags=flags)), to_np(r[0]), "no-codes vs codes path")
         return to_np(r[0]), to_np(r[1]).astype(np.int32)
     return to_np(r)
 
@@ -137,6 +139,8 @@ def _run_olive(antq, x_np, alpha_np, grid_np, outl_np, per_row, no_outlier, flag
     a = torch.from_numpy(np.ascontiguousarray(alpha_np, dtype=np.float32)).to(dev())
     r = antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, want_codes=want_codes, flags=flags)
     if want_codes:
+        assert_bit_equal(to_np(antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, flags=flags)), to_np(r[0]),
+                         "no-codes vs codes path")
         return to_np(r[0]), to_np(r[1]).astype(np.int32)
     return to_np(r)
 
