@@ -49,16 +49,30 @@ constexpr int kNumSms = 148;
 constexpr int kMetaWords = 8;
 constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
 constexpr int kThreads = (kNC + 1 + kNB) * 32;   // consumers | issuer | builders
+#ifndef ANTQS_WINDOW
+#define ANTQS_WINDOW 16
+#endif
+constexpr int kWindow = ANTQS_WINDOW;      // chunks in flight per SM (64 KiB ~ the latency-bandwidth product per SM)
+#ifndef ANTQS_PACE
+#define ANTQS_PACE 256
+#endif
+constexpr int kPace = ANTQS_PACE;          // cycles between two requests of one SM
+#ifndef ANTQS_TEAM
+#define ANTQS_TEAM 2
+#endif
+constexpr int kTeam = ANTQS_TEAM;          // consumer warps sharing one chunk
+constexpr int kTeams = kNC / kTeam;
+static_assert(kNC % kTeam == 0 && kNS % kTeams == 0, "teams meet their stages in lap order");
 constexpr int kRT = 32;                    // row-table ring slots (power of two)
 static_assert(kNS - 1 + 8 <= kRT, "a consumer can be kNS - 1 rows ahead of the slowest one; G <= 8 rows per build");
-static_assert(kNS % kNC == 0, "every consumer meets its stages in lap order");
+static_assert(kNS <= 32, "one issuer lane per stage");
 
 enum : uint32_t { kRowOk = 1u, kRowTies = 2u, kRowFma = 4u };
 
 template <int NT> struct TabGeom {
     static constexpr int NTP = NT + 1;                 // table pitch in words: 4, 8, 16, 32
     static constexpr int G = 32 / NTP;                 // rows built at once by the producer warp
-    static constexpr int kTabBytes = ((6 * NTP + kMetaWords) * 4 + 127) / 128 * 128;
+    static constexpr int kTabBytes = ((7 * NTP + kMetaWords) * 4 + 127) / 128 * 128;
 };
 
 struct StreamParams {
@@ -72,7 +86,9 @@ struct StreamParams {
     int nt_real, mid, ovp_index, n_entries;
     float gmax, lim;
     int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin
-    int stages;         // ring stages in use (<= kNS, multiple of kNP); ANTQ_STAGES experiments
+    int stages;         // ring stages in use (<= kNS); ANTQ_STAGES experiments
+    int window;         // chunks in flight per SM; ANTQ_WINDOW experiments
+    int pace;           // minimum cycles between two requests of one SM; ANTQ_PACE experiments
     unsigned long long *trace;   // ANTQS_TRACE builds: per-CTA timeline (tools/trace_stream.py)
 };
 
@@ -91,6 +107,19 @@ __device__ __forceinline__ unsigned long long antqs_now() {
 #endif
 
 // ---- mbarrier helpers not in antq_common.cuh ------------------------------------------------
+__device__ __forceinline__ bool antqs_mbar_test(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(antq_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void antqs_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
 }
@@ -126,10 +155,10 @@ __device__ __noinline__ void antqs_slow_vec(const AntqCodebook *__restrict__ cb,
 // element (or every vector, when the row's scale is not a positive finite number) is recomputed.
 template <typename T, bool OVP>
 __device__ __noinline__ void antqs_fixup_chunk(const AntqCodebook *__restrict__ cb, float s, float xlim, bool all,
-                                               const uint4 *sv, T *og, int nvec, int lane) {
+                                               const uint4 *sv, T *og, int va, int nvec, int lane) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
-    for (int v = lane; v < nvec; v += 32) {
+    for (int v = va + lane; v < nvec; v += 32) {
         const T *xv = reinterpret_cast<const T *>(sv + v);
         bool special = all;
 #pragma unroll
@@ -138,10 +167,11 @@ __device__ __noinline__ void antqs_fixup_chunk(const AntqCodebook *__restrict__ 
     }
 }
 
-// Exact (X, Xn) for a 16-bit type when the division-free shortcut could not prove them
-// (p = t*s within 16 fp32-ulps of a representable value): at most three divisions.
+// Exact (X, Xn) for a 16-bit type: X = min{x in T : fl32(x / s) >= tpos}, Xn likewise for tneg (>= tpos, a few
+// fp32-ulps above it).  RN_T(fl32(tpos * s)) is within one step of X (tests/xspace_model.py), so two divisions settle
+// it; the walk upward is a safeguard that has never been observed to take more than one step.
 template <typename T>
-__device__ __noinline__ void antqs_x_threshold16_near(float tpos, float tneg, float s, T *xp, T *xn) {
+__device__ __forceinline__ void antqs_x_threshold16(float tpos, float tneg, float s, T *xp, T *xn) {
     typedef AntqType<T> A;
     T c = A::from_f32_rn(__fmul_rn(tpos, s));
     float qc = __fdiv_rn(A::to_f32(c), s);
@@ -192,7 +222,7 @@ template <typename V> __device__ __forceinline__ uint32_t antqs_u32(const V &v) 
 // Producer side: the tables of one row, one lane per threshold.
 // ==================================================================================================
 struct RowTab {
-    uint32_t X, Xn, T2, B, C, D;            // this lane's entry of each table
+    uint32_t X, Xn, T2, B, C, D, Cn;        // this lane's entry of each table
     uint32_t s_bits, flags, xlim, S2, xovp, xovpn;   // uniform over the lanes of one row group
 };
 
@@ -225,13 +255,17 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
     T Xl = A::from_bits(A::kInf), Xnl = A::from_bits(A::kInf), Ol = A::from_bits(0);
     if (row_ok) {
         if (sub < nt_real) {
-            bool near;
-            Xl = antq_x_threshold<T>(tpos, s, &near);
-            Xnl = Xl;
-            if (SYM && near) {
+            if constexpr (sizeof(T) == 2) {
+                // always the exact two-division form, inline: straight-line code on the start-up critical path
+                // (the division-free shortcut saved arithmetic but put a divergent call in front of the first chunk)
+                antqs_x_threshold16<T>(tpos, SYM ? tneg : tpos, s, &Xl, &Xnl);
+                if (!SYM) Xnl = Xl;
+            } else {
+                bool near;
+                Xl = antq_x_threshold<T>(tpos, s, &near);
+                Xnl = Xl;
                 // a negative input can land on the other side of a representable tie
-                if constexpr (sizeof(T) == 2) antqs_x_threshold16_near<T>(tpos, tneg, s, &Xl, &Xnl);
-                else Xnl = antq_x_threshold_exact<T>(tneg, s);
+                if (SYM && near) Xnl = antq_x_threshold_exact<T>(tneg, s);
             }
         }
         if (sub <= nt_real) Ol = A::from_f32_rn(__fmul_rn(lev, s));
@@ -246,7 +280,7 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
     t.flags = (row_ok ? kRowOk : 0u) | (ties ? kRowTies : 0u);
     const float xl = __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);    // conservative window in x-space
     t.xlim = antqs_word<T>(A::from_f32_rz(xl));
-    t.S2 = 0; t.B = 0; t.C = 0; t.D = 0;
+    t.S2 = 0; t.B = 0; t.C = 0; t.D = 0; t.Cn = 0;
     {
         const int oi = p.ovp_index;
         const bool has = OVP && oi >= 0 && oi < NT;
@@ -266,7 +300,7 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         t.T2 = e | (e << 16);
 
         // FMA-pipe twin
-        bool ok = row_ok && !ties && NT <= 15 && !(p.debug & 16);
+        bool ok = row_ok && NT <= 15 && (!ties || NT <= 7) && !(p.debug & 16);
         // S = 2^k with xlim * S in [2^13, 2^14): every in-window |x| stays finite after scaling
         int k = 13 - (int)((__float_as_uint(xl) >> 23) & 0xff) + 127;
         k = k > 15 ? 15 : (k < -14 ? -14 : k);
@@ -286,8 +320,8 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
                 const int eb = 254 - eu - k;
                 Bv = (eb >= 1 && eb <= 254) ? __uint_as_float((unsigned)eb << 23) : 0.0f;      // 1 / (u S)
                 Cv = -__fmul_rn(A::to_f32(P), Bfull);
-                ok = ok && Bv >= 6.103515625e-05f && Bv <= 32768.0f && fabsf(Cv) <= 2048.0f;
-                if (sizeof(T) == 2 && A::kInf == 0x7f80u) ok = ok && fabsf(Cv) <= 256.0f;  // bf16: 8-bit integers
+                ok = ok && Bv >= 6.103515625e-05f && Bv <= 32768.0f && fabsf(Cv) <= 2047.0f;
+                if (sizeof(T) == 2 && A::kInf == 0x7f80u) ok = ok && fabsf(Cv) <= 255.0f;  // bf16: 8-bit integers
             }
         }
         // D_i = O[i+1] - O[i] must be exactly representable (fp32 difference of two 16-bit values is exact)
@@ -299,6 +333,8 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         t.D = antqs_word<T>(sub < nt_real ? D : A::from_bits(0));
         t.B = antqs_word<T>(A::from_f32_rn(Bv));
         t.C = antqs_word<T>(A::from_f32_rn(Cv));
+        // negative inputs of a tie threshold compare against X + 1 ulp:  sat((|x| - X) / u) = sat(|x| / u + (C - 1))
+        t.Cn = antqs_word<T>(A::from_f32_rn(A::bits(Xl) != A::bits(Xnl) ? __fsub_rn(Cv, 1.0f) : Cv));
         t.S2 = antqs_word<T>(A::from_f32_rn(S));
         if (fma_ok) t.flags |= kRowFma;
     } else {
@@ -321,34 +357,43 @@ template <int N> __device__ __forceinline__ void load_words(uint32_t (&dst)[N], 
     }
 }
 
-enum { kModeAlu = 0, kModeTies = 1, kModeMix = 2 };
+enum { kModeAlu = 0, kModeTies = 1, kModeMix = 2, kModeTiesMix = 3 };
 
 // 16-bit element types: one 32-bit register = two elements (low half = even flat index).
+//   kModeAlu      every pair on the ALU pipe
+//   kModeMix      tie-free row with exact FMA twins: pairs split between the ALU and the FMA pipe
+//   kModeTies     row with representable ties (negative inputs use Xn), ALU pipe only
+//   kModeTiesMix  the same with FMA twins: negative inputs select C - 1 (one LOP3) and the compare / accumulate
+//                 run on the FMA pipe; one pair of four stays on the ALU pipe
 template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
     typedef typename Pack2<T>::v2 v2;
     static constexpr int NTP = NT + 1;
+    static constexpr bool TIES = SYM && (MODE == kModeTies || MODE == kModeTiesMix);
+    static constexpr bool FMA = MODE == kModeMix || MODE == kModeTiesMix;
     uint32_t X[NT + 1];                       // [NT] unused
     uint32_t E[NT + 1];                       // [NT] = O[0]
-    uint32_t Xn[MODE == kModeTies ? NT + 1 : 1];
-    uint32_t Bf[MODE == kModeMix ? NT + 1 : 1], Cf[MODE == kModeMix ? NT + 1 : 1], Df[MODE == kModeMix ? NT + 1 : 1];
+    uint32_t Xn[TIES ? NT + 1 : 1];
+    uint32_t Bf[FMA ? NT + 1 : 1], Cf[FMA ? NT + 1 : 1], Df[FMA ? NT + 1 : 1];
+    uint32_t Cn[(FMA && TIES) ? NT + 1 : 1];
     uint32_t S2, xovp, xovpn;
     v2 mx;                                    // running max of |x| (NaN-propagating)
 
     __device__ __forceinline__ void load(const uint32_t *tab, uint32_t s2, uint32_t xo, uint32_t xon) {
         load_words<NT + 1>(X, tab);
         load_words<NT + 1>(E, tab + 2 * NTP);
-        if constexpr (MODE == kModeTies) load_words<NT + 1>(Xn, tab + NTP);
-        if constexpr (MODE == kModeMix) {
+        if constexpr (TIES) load_words<NT + 1>(Xn, tab + NTP);
+        if constexpr (FMA) {
             load_words<NT + 1>(Bf, tab + 3 * NTP);
             load_words<NT + 1>(Cf, tab + 4 * NTP);
             load_words<NT + 1>(Df, tab + 5 * NTP);
         }
+        if constexpr (FMA && TIES) load_words<NT + 1>(Cn, tab + 6 * NTP);
         S2 = s2; xovp = xo; xovpn = xon;
         mx = Pack2<T>::from_u32(0u);
     }
 
     __device__ __forceinline__ uint32_t ovp_mask(v2 a2, uint32_t neg) const {
-        const uint32_t t = (SYM && MODE == kModeTies) ? ((neg & xovpn) | (~neg & xovp)) : xovp;
+        const uint32_t t = TIES ? ((neg & xovpn) | (~neg & xovp)) : xovp;
         const uint32_t mo = __hge2_mask(a2, Pack2<T>::from_u32(t));      // element is an outlier
         const uint32_t sw = __byte_perm(mo, 0, 0x1032);                  // swap halves
         return sw & ~(mo & 0x0000ffffu);   // odd dies if even is outlier; even dies if only odd is
@@ -361,12 +406,12 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
         const v2 a2 = SYM ? ab : x2;
         mx = __hmax2_nan(mx, ab);
         uint32_t neg = 0;
-        if (SYM && MODE == kModeTies) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));   // 0xffff where x < 0
+        if (TIES) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));       // 0xffff where x < 0
         uint32_t q = SYM ? 0u : E[NT];
 #pragma unroll
         for (int i = 0; i < NT; i++) {
             uint32_t t = X[i];
-            if constexpr (SYM && MODE == kModeTies) t = (neg & Xn[i]) | (~neg & X[i]);
+            if constexpr (TIES) t = (neg & Xn[i]) | (~neg & X[i]);
             const uint32_t m = __hge2_mask(a2, Pack2<T>::from_u32(t));
             q ^= m & E[i];
         }
@@ -375,16 +420,20 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
         return q;
     }
 
-    // FMA pipe: saturating-FMA compare + exact accumulate (tie-free rows only)
+    // FMA pipe: saturating-FMA compare + exact accumulate
     __device__ __forceinline__ uint32_t pair_fma(uint32_t xb) {
         const v2 x2 = Pack2<T>::from_u32(xb);
         const v2 ab = __habs2(x2);
         mx = __hmax2_nan(mx, ab);
+        uint32_t neg = 0;
+        if (TIES) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));
         const v2 xs = __hmul2(SYM ? ab : x2, Pack2<T>::from_u32(S2));
         v2 q = Pack2<T>::from_u32(E[NT]);
 #pragma unroll
         for (int i = 0; i < NT; i++) {
-            const v2 m = __hfma2_sat(xs, Pack2<T>::from_u32(Bf[i]), Pack2<T>::from_u32(Cf[i]));
+            uint32_t c = Cf[i];
+            if constexpr (FMA && TIES) c = (neg & Cn[i]) | (~neg & Cf[i]);
+            const v2 m = __hfma2_sat(xs, Pack2<T>::from_u32(Bf[i]), Pack2<T>::from_u32(c));
             q = __hfma2(m, Pack2<T>::from_u32(Df[i]), q);
         }
         uint32_t qb;
@@ -395,7 +444,7 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
         } else {
             qb = antqs_u32(q);
         }
-        if (OVP) qb &= ~ovp_mask(SYM ? ab : x2, 0u);
+        if (OVP) qb &= ~ovp_mask(SYM ? ab : x2, neg);
         return qb;
     }
 
@@ -403,8 +452,9 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
         if (debug & 2) return r;
         uint4 q;
         q.x = pair_alu(r.x);
-        q.z = pair_alu(r.z);
-        if constexpr (MODE == kModeMix) {
+        if constexpr (MODE == kModeTiesMix) q.z = pair_fma(r.z);
+        else q.z = pair_alu(r.z);
+        if constexpr (FMA) {
             q.y = pair_fma(r.y);
             q.w = pair_fma(r.w);
         } else {
@@ -477,12 +527,13 @@ template <int NT, bool SYM, bool OVP> struct Chain32 {
 
 // One chunk from shared memory to global memory: two vectors per lane per iteration, then the remainder.
 template <typename CH>
-__device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uint4 *sv, uint4 *og, int nvec, int lane,
-                                          uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim, int debug) {
+__device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uint4 *sv, uint4 *og, int va, int nvec,
+                                          int lane, uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim, int debug) {
+    // vectors [va, nvec) of the chunk (this warp's part)
     ch.load(tab, s2, xo, xon);
-    const uint4 *sp = sv + lane;
-    uint4 *op = og + lane;
-    const int nfull = nvec >> 6;
+    const uint4 *sp = sv + va + lane;
+    uint4 *op = og + va + lane;
+    const int nfull = (nvec - va) >> 6;
 #pragma unroll 1
     for (int it = 0; it < nfull; ++it) {
         const uint4 r0 = sp[0], r1 = sp[32];                   // LDS.128, conflict free
@@ -493,7 +544,7 @@ __device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uin
         sp += 64; op += 64;
     }
 #pragma unroll 1
-    for (int v = (nfull << 6) + lane; v < nvec; v += 32) {
+    for (int v = va + (nfull << 6) + lane; v < nvec; v += 32) {
         const uint4 q0 = ch.vec(*sp, debug);
         antq_stg_stream(op, q0);
         sp += 32; op += 32;
@@ -522,8 +573,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     unsigned char *ring = antqs_smem + (size_t)kNS * kChunkMax;                // kRT row-table slots
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kRT * kTabBytes);
     uint64_t *empty = full + kNS;
-    unsigned *built = reinterpret_cast<unsigned *>(empty + kNS);               // [kNB] row groups finished per builder
-    unsigned *cons_row = built + kNB;                                          // [kNC] CTA-local row each consumer is on
+    unsigned *built = reinterpret_cast<unsigned *>(empty + kNS);               // [kRT] lap + 1 of the group in each ring slot
+    unsigned *cons_row = built + kRT;                                          // [kNC] CTA-local row each consumer is on
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // equal contiguous share of the chunk list (32-bit: the launcher refuses tensors of more than 2^31 chunks)
@@ -532,62 +583,125 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     const unsigned cpr = (unsigned)p.chunks_per_row;
     const unsigned row_begin = c_begin / cpr;
     const AntqCodebook *__restrict__ cb = p.cb;
+    static_assert(kRT + kNC <= kThreads, "one thread per flag word at start-up");
 
     if (warp == 0) ANTQS_TR(0);
+    // Programmatic dependent launch: the next kernel in the stream may be scheduled onto SMs as our CTAs leave them ...
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x < kNS) {
         antq_mbar_init(full + threadIdx.x, 1);
-        antq_mbar_init(empty + threadIdx.x, 1);
+        antq_mbar_init(empty + threadIdx.x, kTeam);
     }
-    if (threadIdx.x < kNB + kNC) built[threadIdx.x] = 0;                       // built[] and cons_row[] are contiguous
+    if (threadIdx.x < kRT + kNC) built[threadIdx.x] = 0;                       // built[] and cons_row[] are contiguous
     __syncthreads();
+    // ... and everything above overlapped the tail of the previous kernel; nothing it may have written (x, alpha, the
+    // codebook) or may still be reading (out) is touched before it has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == 0) ANTQS_TR(1);
+
+    // ---- row tables: G rows per build pass, kept in a ring of kRT rows = GS group slots ----
+    constexpr int GS = kRT / G;
+    const unsigned last_row = (unsigned)(p.rows - 1);
+    const unsigned row_last = (c_begin + (unsigned)n - 1u) / cpr;
+    const int ngroups = p.alpha_per_row ? (int)((row_last - row_begin) / G + 1) : 1;
+    // Groups [0, n_pro) are built in the PROLOGUE by every warp except the issuer, one group each, all at once: the
+    // consumers have nothing to do until the first chunk lands, and a builder warp that has to share its scheduler
+    // with three busy consumers is ~4x slower per pass than at start-up (profiles/r02_notes.md).  Later groups (a CTA
+    // with more than kRT rows) are made by the builder warps as the consumers free ring slots.
+    const int n_pro = min(ngroups, min(GS, kNC + kNB));
+    auto build_group = [&](int g, bool tr) {
+        const int sub = lane % NTP, grp = lane / NTP;
+        const int nt_real = p.nt_real;
+        const float inf = __int_as_float(0x7f800000);
+        unsigned r = row_begin + (unsigned)(g * G + grp);
+        r = r > last_row ? last_row : r;
+        const float alpha = __ldg(p.alpha + (p.alpha_per_row ? r : 0));
+        const float tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
+        const float tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : tpos;
+        const float lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
+        if (tr) ANTQS_TR(3);
+        RowTab tab;
+        build_tables<T, NT, SYM, OVP>(tab, p, alpha, tpos, tneg, lev, sub, grp, tr);
+        uint32_t *st = reinterpret_cast<uint32_t *>(ring + (size_t)((g * G + grp) & (kRT - 1)) * kTabBytes);
+        st[sub] = tab.X;
+        st[NTP + sub] = tab.Xn;
+        st[2 * NTP + sub] = tab.T2;
+        st[3 * NTP + sub] = tab.B;
+        st[4 * NTP + sub] = tab.C;
+        st[5 * NTP + sub] = tab.D;
+        st[6 * NTP + sub] = tab.Cn;
+        if (sub == 0) {
+            uint4 *m = reinterpret_cast<uint4 *>(st + 7 * NTP);
+            m[0] = make_uint4(tab.s_bits, tab.flags, tab.xlim, tab.S2);
+            m[1] = make_uint4(tab.xovp, tab.xovpn, 0u, 0u);
+        }
+        __syncwarp();
+        if (lane == 0) antqs_st_release(built + (g % GS), (unsigned)(g / GS) + 1u);   // release: tables visible
+        if (tr) ANTQS_TR(4);
+    };
+    if (warp != kNC) {
+        const int br = warp < kNC ? warp : warp - 1;                  // rank among the warps that build
+        if (br < n_pro) build_group(br, br == 0);
+    }
 
     if (warp == kNC) {
         // ------------------------------ issuer ------------------------------
-        // Walks this CTA's chunks in order; a chunk goes in flight (one TMA bulk copy) the moment its stage is free.
-        unsigned row = row_begin;
-        int idx = (int)(c_begin - row * cpr);
-        const T *src_row = reinterpret_cast<const T *>(p.x) + (long long)row * p.cols;
-        int stage = 0;
-        unsigned parity = 1;                                          // a fresh barrier passes a parity-1 wait
-        for (int k = 0; k < n; ++k) {
-            antq_mbar_wait(empty + stage, parity);
-            if (lane == 0) {
-                const long long col0 = (long long)idx * p.chunk_elems;
+        // Lane L owns stage L and the chunks L, L + stages, ... that pass through it.  Chunks go in flight (one TMA
+        // bulk copy each) in order, as soon as their stage is free, but never more than `window` at a time: requesting
+        // the whole ring at start-up makes every SM's FIRST chunk wait behind ~30 MB of other requests (measured,
+        // profiles/r02_notes.md); a window of a few chunks per SM already covers the HBM latency-bandwidth product.
+        const int ns = p.stages;
+        int k = lane;                                                 // this lane's next chunk
+        unsigned epar = 1, fpar = 0;                                  // a fresh barrier passes a parity-1 test
+        bool active = lane < ns && k < n;
+        bool inflight = false;                                        // issued, not yet seen landed
+        // pacing: at most one more chunk per `pace` cycles (only bites during the first microseconds, when every
+        // stage is free and there are no stores yet)
+        long long next_t = clock64();
+        int allowed = 0, issued = 0;
+        while (__any_sync(0xffffffffu, active)) {
+            if (inflight && antqs_mbar_test(full + lane, fpar)) inflight = false;
+            {
+                const long long now = __shfl_sync(0xffffffffu, clock64(), 0);
+                while (now >= next_t && allowed - issued < 64) { ++allowed; next_t += p.pace; }
+            }
+            int budget = p.window - __popc(__ballot_sync(0xffffffffu, inflight));
+            budget = min(budget, allowed - issued);
+            const int kmin = __reduce_min_sync(0xffffffffu, active ? k : 0x7fffffff);
+            const bool go = active && (k - kmin) < budget && antqs_mbar_test(empty + lane, epar);
+            if (go) {
+                const unsigned c = c_begin + (unsigned)k;
+                const unsigned row = c / cpr;
+                const long long col0 = (long long)(c - row * cpr) * p.chunk_elems;
                 const long long remain = p.cols - col0;
                 const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
                 const unsigned bytes = (unsigned)(n_el / VEC) * 16u;
                 // (no fence.proxy.async: the consumer's reads of this stage are ordered before this copy by its
-                //  release-arrive on `empty` and the acquire-wait above, as in every TMA load pipeline)
-                if (bytes) antq_bulk_g2s(antqs_smem + (size_t)stage * kChunkMax, src_row + col0, bytes, full + stage);
-                else antqs_mbar_arrive(full + stage);
+                //  release-arrive on `empty` and the acquire-test above, as in every TMA load pipeline)
+                if (bytes)
+                    antq_bulk_g2s(antqs_smem + (size_t)lane * kChunkMax,
+                                  reinterpret_cast<const T *>(p.x) + (long long)row * p.cols + col0, bytes, full + lane);
+                else
+                    antqs_mbar_arrive(full + lane);
+#ifdef ANTQS_TRACE
+                if (p.trace && k < kTraceChunks) p.trace[(size_t)blockIdx.x * kTraceStride + 8 + 4 * k] = antqs_now();
+#endif
+                inflight = true;
+                fpar = epar ^ 1u;                                      // parity of the phase just started on `full`
+                k += ns;
+                epar ^= 1u;
+                active = k < n;
             }
-            ANTQS_TRK(k, 0);
-            if (++idx == (int)cpr) { idx = 0; src_row += p.cols; }
-            if (++stage == p.stages) { stage = 0; parity ^= 1u; }
+            const unsigned went = __ballot_sync(0xffffffffu, go);
+            issued += __popc(went);
+            if (!went) __nanosleep(32);
         }
     } else if (warp > kNC) {
         // ------------------------------ table builders ------------------------------
-        // Builder b makes the tables of row groups b, b + kNB, ... (G rows per pass, one lane per threshold) and
-        // stores them in the row-table ring; it runs ahead of the consumers by up to kRT rows.
+        // Builder b makes the tables of row groups n_pro + b, n_pro + b + kNB, ... (G rows per pass, one lane per
+        // threshold) and stores them in the row-table ring; the builders run ahead of the consumers by up to kRT rows.
         const int b = warp - kNC - 1;
-        const int sub = lane % NTP, grp = lane / NTP;
-        const int nt_real = p.nt_real;
-        const float inf = __int_as_float(0x7f800000);
-        const unsigned last_row = (unsigned)(p.rows - 1);
-        const unsigned row_last = (c_begin + (unsigned)n - 1u) / cpr;
-        const int ngroups = p.alpha_per_row ? (int)((row_last - row_begin) / G + 1) : 1;
-        auto alpha_of = [&](int g) {
-            unsigned r = row_begin + (unsigned)(g * G + grp);
-            r = r > last_row ? last_row : r;
-            return __ldg(p.alpha + (p.alpha_per_row ? r : 0));
-        };
-        float alpha_next = alpha_of(b);                               // prefetched one pass ahead
-        const float tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
-        const float tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : tpos;
-        const float lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
-        unsigned done = 0;
-        for (int g = b; g < ngroups; g += kNB) {
+        for (int g = n_pro + b; g < ngroups; g += kNB) {
             const int r0 = g * G;                                     // first CTA-local row of the group
             if (r0 + G > kRT) {
                 // the slot of row r is reused by row r + kRT: wait until every consumer has moved past row r0 + G - 1 - kRT
@@ -600,36 +714,20 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                     __nanosleep(200);
                 }
             }
-            const float alpha = alpha_next;
-            if (g + kNB < ngroups) alpha_next = alpha_of(g + kNB);
-            const bool tr = (b == 0 && g == 0);
-            if (tr) ANTQS_TR(3);
-            RowTab tab;
-            build_tables<T, NT, SYM, OVP>(tab, p, alpha, tpos, tneg, lev, sub, grp, tr);
-            uint32_t *st = reinterpret_cast<uint32_t *>(ring + (size_t)((r0 + grp) & (kRT - 1)) * kTabBytes);
-            st[sub] = tab.X;
-            st[NTP + sub] = tab.Xn;
-            st[2 * NTP + sub] = tab.T2;
-            st[3 * NTP + sub] = tab.B;
-            st[4 * NTP + sub] = tab.C;
-            st[5 * NTP + sub] = tab.D;
-            if (sub == 0) {
-                uint4 *m = reinterpret_cast<uint4 *>(st + 6 * NTP);
-                m[0] = make_uint4(tab.s_bits, tab.flags, tab.xlim, tab.S2);
-                m[1] = make_uint4(tab.xovp, tab.xovpn, 0u, 0u);
-            }
-            __syncwarp();
-            ++done;
-            if (lane == 0) antqs_st_release(built + b, done);          // release: the group's tables are visible
-            if (tr) ANTQS_TR(4);
+            build_group(g, false);
         }
     } else {
         // ------------------------------ consumers ------------------------------
-        // Consumer w owns chunks w, w + kNC, ...: with stages % kNC == 0 it meets every stage it uses in lap order, so
-        // a parity wait can never alias a phase two laps back (a shared work counter could run a lap ahead).
-        int stage = warp;
+        // The consumers form kTeams teams of kTeam warps (one warp per scheduler).  Team t owns chunks t, t + kTeams, ...
+        // in order, and every warp of the team takes a fixed share of each chunk (whole 64-vector blocks): the latency of
+        // a chunk -- and with it the tail after the last chunk has landed, and the idle time when chunks do not divide
+        // evenly among warps -- is kTeam times shorter than with one warp per chunk, with no shared work counter.
+        // stages % kTeams == 0, so a team meets every stage it uses in lap order and a parity wait cannot alias.
+        const int team = warp / kTeam, part = warp % kTeam;
+        constexpr int nparts = kTeam;
+        int stage = team;
         unsigned parity = 0;
-        for (int k = warp; k < n; k += kNC, stage += kNC) {
+        for (int k = team; k < n; k += kTeams, stage += kTeams) {
             if (stage >= p.stages) { stage -= p.stages; parity ^= 1u; }
             const unsigned c = c_begin + (unsigned)k;
             const unsigned row = c / cpr;
@@ -638,14 +736,14 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             if (lane == 0) antqs_st_release(cons_row + warp, rl);              // builders may recycle slots of rows < rl
             {
                 const unsigned g = rl / G;
-                const unsigned *flag = built + (g % kNB);
-                const unsigned need = g / kNB + 1u;
+                const unsigned *flag = built + (g % GS);
+                const unsigned need = g / GS + 1u;
                 while (antqs_ld_acquire(flag) < need) __nanosleep(100);         // only at start-up in practice
             }
             ANTQS_TRK(k, 1);
             const uint32_t *tab = reinterpret_cast<const uint32_t *>(ring + (size_t)(rl & (kRT - 1)) * kTabBytes);
-            const uint4 m0 = reinterpret_cast<const uint4 *>(tab + 6 * NTP)[0];
-            const uint4 m1 = reinterpret_cast<const uint4 *>(tab + 6 * NTP)[1];
+            const uint4 m0 = reinterpret_cast<const uint4 *>(tab + 7 * NTP)[0];
+            const uint4 m1 = reinterpret_cast<const uint4 *>(tab + 7 * NTP)[1];
             const float s = __uint_as_float(m0.x);
             const uint32_t flags = m0.y, xlim = m0.z;
             const long long col0 = (long long)idx * p.chunk_elems;
@@ -657,38 +755,44 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             T *og = reinterpret_cast<T *>(p.out) + base;
             antq_mbar_wait(full + stage, parity);                      // the chunk has landed in shared memory
             ANTQS_TRK(k, 2);
+            const int nblk = (nvec + 63) >> 6;
+            const int va = ((part * nblk) / nparts) << 6;
+            const int vb = min((((part + 1) * nblk) / nparts) << 6, nvec);
             bool special = !(flags & kRowOk);
-            if (nvec > 0 && !special) {
+            if (vb > va && !special) {
                 uint4 *ov = reinterpret_cast<uint4 *>(og);
                 if constexpr (sizeof(T) == 2) {
-                    if (flags & kRowTies) {
+                    if ((flags & kRowTies) && (flags & kRowFma)) {
+                        Chain16<T, NT, SYM, OVP, (SYM && NT <= 7 ? kModeTiesMix : kModeTies)> ch;
+                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    } else if (flags & kRowTies) {
                         Chain16<T, NT, SYM, OVP, kModeTies> ch;
-                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else if (flags & kRowFma) {
                         Chain16<T, NT, SYM, OVP, (NT <= 15 ? kModeMix : kModeAlu)> ch;
-                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else {
                         Chain16<T, NT, SYM, OVP, kModeAlu> ch;
-                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     }
                 } else {
                     Chain32<NT, SYM, OVP> ch;
-                    special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                 }
             }
-            if (nvec > 0 && __any_sync(0xffffffffu, special)) {
+            if (vb > va && __any_sync(0xffffffffu, special)) {
                 float xl;
                 if constexpr (sizeof(T) == 2) xl = A::to_f32(A::from_bits((typename A::bits_t)(xlim & 0xffffu)));
                 else xl = __uint_as_float(xlim);
-                antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, nvec, lane);
+                antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, va, vb, lane);
             }
             // ragged tail (only a per-tensor view can have one: rows == 1): straight from global memory
-            if (tail > 0 && lane == 0) {
+            if (tail > 0 && lane == 0 && part == nparts - 1) {
                 const T *xg = reinterpret_cast<const T *>(p.x) + base + (long long)nvec * VEC;
                 antqs_slow_vec<T, OVP>(cb, s, xg, og + (long long)nvec * VEC, tail);
             }
             __syncwarp();                                              // every lane is done with this stage
-            if (lane == 0) antqs_mbar_arrive(empty + stage);
+            if (lane == 0) antqs_mbar_arrive(empty + stage);           // the stage is free once the whole team has arrived
             ANTQS_TRK(k, 3);
         }
         if (lane == 0) antqs_st_release(cons_row + warp, 0xffffffffu);  // done: never holds a table slot again
@@ -700,15 +804,27 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
 
 template <typename T, int NT, bool SYM, bool OVP> int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_stream_kernel<T, NT, SYM, OVP>;
-    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + 2 * kNS * 8 + (kNB + kNC) * 4 + 16;
+    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + 2 * kNS * 8 + (kRT + kNC) * 4 + 16;
     static bool configured = false;      // per instantiation; the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    kernel<<<dim3((unsigned)ctas), dim3(kThreads), smem, st>>>(p);
-    cudaError_t e = cudaGetLastError();
+    static int pdl = -1;
+    if (pdl < 0) { const char *v = getenv("ANTQ_PDL"); pdl = (v && atoi(v) == 0) ? 0 : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess)
         fprintf(stderr, "antq: stream kernel launch failed: %s (grid %d, block %d, smem %d, chunks %u)\n",
                 cudaGetErrorString(e), ctas, kThreads, smem, p.total_chunks);
@@ -745,13 +861,17 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
     const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
     const int es = dtype == ANTQ_F32 ? 4 : 2;
-    static int dbg = -1, chunk_env = 0, stages_env = 0;
+    static int dbg = -1, chunk_env = 0, stages_env = 0, window_env = 0, pace_env = 0;
     if (dbg < 0) {
         const char *e = getenv("ANTQ_DEBUG");
         const char *c = getenv("ANTQ_CHUNK");
         const char *g = getenv("ANTQ_STAGES");
         chunk_env = c ? atoi(c) : 0;
         stages_env = g ? atoi(g) : 0;
+        const char *w = getenv("ANTQ_WINDOW");
+        window_env = w ? atoi(w) : 0;
+        const char *pc = getenv("ANTQ_PACE");
+        pace_env = pc ? atoi(pc) : 0;
         dbg = e ? atoi(e) : 0;
     }
     StreamParams p;
@@ -781,7 +901,9 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     p.nt_real = nt; p.mid = info->mid; p.ovp_index = info->ovp_index; p.n_entries = info->n_entries;
     p.gmax = info->gmax; p.lim = info->lim;
     p.debug = dbg;
-    p.stages = (stages_env >= kNC && stages_env <= kNS && stages_env % kNC == 0) ? stages_env : kNS;
+    p.stages = (stages_env >= kTeams && stages_env <= kNS && stages_env % kTeams == 0) ? stages_env : kNS;
+    p.window = window_env >= 1 ? window_env : kWindow;
+    p.pace = pace_env >= 1 ? pace_env : kPace;
     p.trace = antqs_trace_buffer;
     const int ctas = (int)(p.total_chunks < (unsigned)kNumSms ? p.total_chunks : (unsigned)kNumSms);
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;

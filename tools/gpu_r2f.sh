@@ -1,0 +1,18 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+O=gpurun_out/r2f_bench.jsonl; : > $O
+qb() { timeout 120 python tools/quick_bench.py "$@" 2>&1 | tail -1 | tee -a $O; }
+qb --tag new
+for w in 4 6 10 12 16 24; do ANTQ_WINDOW=$w qb --tag w$w; done
+ANTQ_DEBUG=2 qb --tag new_copy
+ANTQ_DEBUG=2 ANTQ_WINDOW=12 qb --tag copy_w12
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -4
+ANTQ_LIB_SUFFIX=_trace timeout 120 python tools/trace_stream.py 2>&1 | tail -32 | tee gpurun_out/trace_f.txt
+ANTQ_CHUNK=4096 qb --tag c4k
+ANTQ_CHUNK=4096 ANTQ_WINDOW=16 qb --tag c4k_w16
+qb --alpha-mult 1.0 --tag new_a1.0
+qb --per-tensor --tag new_pt
+qb --dtype f32 --tag new_f32
+qb --kind int --tag new_int
+qb --olive --tag new_olive
+qb --rows 8192 --cols 8192 --nb 4 --tag new_8k
+qb --rows 1024 --cols 1024 --nb 16 --tag new_1k
