@@ -8,17 +8,24 @@
 // exhaustive fp16 inputs in tests/test_xspace_model.py).  Per 32-bit register (two 16-bit values):
 //   ALU-pipe chain   m = HSET2.BM(|x| >= X_i);  q ^= m & E_i          (E_i = O_{i+1} xor O_i)
 //   FMA-pipe chain   m = HFMA2.SAT(|x|S, B_i, C_i);  q = HFMA2(m, D_i, q)   (exact, see build_tables)
-// and the pairs of every vector are split between the two chains because both pipes are half-rate.
+// and the pairs of every vector are split between the two chains: every op class issues at most every
+// other cycle, and the scheduler only reaches ~1 instruction/cycle when consecutive instructions of a
+// warp go to different classes (tools/probe/pipe_probe.cu).
 //
-// Execution shape (B200): 148 CTAs, one per SM, each owning an equal contiguous range of chunks
-// (<= 8 KiB pieces that never straddle a row).  Warp 0 is the PRODUCER: it walks the range, puts
-// every chunk in flight with one TMA bulk copy (cp.async.bulk -> shared memory, completion on the
-// stage's `full` mbarrier) as soon as the stage's `empty` mbarrier allows, and -- while the bytes are
-// in flight -- builds the row's tables (thresholds, outputs, FMA twins), lane-parallel over the
-// thresholds of up to 32/(NT+1) rows at once, and publishes them next to the data in the same stage.
-// The other warps are CONSUMERS: they take the next chunk number from a shared counter, wait for its
-// stage, pull the tables into registers, run the chains from shared memory straight to global
-// memory (LDS.128 -> STG.128), and release the stage.  No CTA-wide barrier after start-up.
+// Execution shape (B200): 148 persistent CTAs, one per SM, each owning an equal contiguous range of
+// chunks (<= 4 KiB pieces that never straddle a row) -- found by measurement, profiles/r01_notes.md:
+//   * 12 CONSUMER warps (3 per scheduler).  Each owns two private 4 KiB stages in shared memory and
+//     double-buffers: it claims the next chunk from a CTA-wide counter, puts it in flight with one
+//     TMA bulk copy (cp.async.bulk -> shared memory, completion on the stage's mbarrier), then
+//     computes the chunk that has already landed: LDS.128 -> chains in registers -> STG.128.  The
+//     warp that frees a stage is the one that refills it, so there is no producer warp to starve and
+//     no `empty` barrier; an SM keeps 12 x 4 KiB outstanding -- about the HBM latency-bandwidth
+//     product -- and never floods the memory system at start-up.
+//   * the per-row tables (thresholds, outputs, FMA twins) are built lane-parallel, 32/(NT+1) rows
+//     per pass, into a 32-row ring in shared memory: in the PROLOGUE by every warp at once (the
+//     consumers have nothing to do until their first chunk lands), afterwards by 3 BUILDER warps that
+//     follow the consumers around the ring.  Consumers read them with broadcast LDS.128.
+//   * programmatic dependent launch: barrier set-up of launch N+1 overlaps the tail of launch N.
 //
 // Out-of-window values (|d| > lim, NaN, Inf) are detected with one running packed max per register;
 // the chunk is still in shared memory when the test fires, so a cold pass recomputes exactly those
@@ -36,36 +43,21 @@ namespace {
 #ifndef ANTQS_BUILDERS
 #define ANTQS_BUILDERS 3
 #endif
-#ifndef ANTQS_STAGES
-#define ANTQS_STAGES 24
+#ifndef ANTQS_RING
+#define ANTQS_RING 2
 #endif
 #ifndef ANTQS_CHUNK
-#define ANTQS_CHUNK 8192
+#define ANTQS_CHUNK 4096
 #endif
 constexpr int kNC = ANTQS_CONSUMERS;      // consumer warps per CTA
-constexpr int kNS = ANTQS_STAGES;         // ring stages per CTA
+constexpr int kRing = ANTQS_RING;         // private ring stages per consumer warp
+constexpr int kNS = kNC * kRing;          // stages per CTA
 constexpr int kChunkMax = ANTQS_CHUNK;    // bytes of tensor per stage
 constexpr int kNumSms = 148;
 constexpr int kMetaWords = 8;
 constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
-constexpr int kThreads = (kNC + 1 + kNB) * 32;   // consumers | issuer | builders
-#ifndef ANTQS_WINDOW
-#define ANTQS_WINDOW 16
-#endif
-constexpr int kWindow = ANTQS_WINDOW;      // chunks in flight per SM (64 KiB ~ the latency-bandwidth product per SM)
-#ifndef ANTQS_PACE
-#define ANTQS_PACE 256
-#endif
-constexpr int kPace = ANTQS_PACE;          // cycles between two requests of one SM
-#ifndef ANTQS_TEAM
-#define ANTQS_TEAM 2
-#endif
-constexpr int kTeam = ANTQS_TEAM;          // consumer warps sharing one chunk
-constexpr int kTeams = kNC / kTeam;
-static_assert(kNC % kTeam == 0 && kNS % kTeams == 0, "teams meet their stages in lap order");
+constexpr int kThreads = (kNC + kNB) * 32;       // consumers | builders
 constexpr int kRT = 32;                    // row-table ring slots (power of two)
-static_assert(kNS - 1 + 8 <= kRT, "a consumer can be kNS - 1 rows ahead of the slowest one; G <= 8 rows per build");
-static_assert(kNS <= 32, "one issuer lane per stage");
 
 enum : uint32_t { kRowOk = 1u, kRowTies = 2u, kRowFma = 4u };
 
@@ -86,9 +78,6 @@ struct StreamParams {
     int nt_real, mid, ovp_index, n_entries;
     float gmax, lim;
     int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin
-    int stages;         // ring stages in use (<= kNS); ANTQ_STAGES experiments
-    int window;         // chunks in flight per SM; ANTQ_WINDOW experiments
-    int pace;           // minimum cycles between two requests of one SM; ANTQ_PACE experiments
     unsigned long long *trace;   // ANTQS_TRACE builds: per-CTA timeline (tools/trace_stream.py)
 };
 
@@ -107,19 +96,6 @@ __device__ __forceinline__ unsigned long long antqs_now() {
 #endif
 
 // ---- mbarrier helpers not in antq_common.cuh ------------------------------------------------
-__device__ __forceinline__ bool antqs_mbar_test(uint64_t *bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(antq_smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void antqs_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
 }
@@ -572,9 +548,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     extern __shared__ __align__(128) unsigned char antqs_smem[];
     unsigned char *ring = antqs_smem + (size_t)kNS * kChunkMax;                // kRT row-table slots
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kRT * kTabBytes);
-    uint64_t *empty = full + kNS;
-    unsigned *built = reinterpret_cast<unsigned *>(empty + kNS);               // [kRT] lap + 1 of the group in each ring slot
+    unsigned *built = reinterpret_cast<unsigned *>(full + kNS);               // [kRT] lap + 1 of the group in each ring slot
     unsigned *cons_row = built + kRT;                                          // [kNC] CTA-local row each consumer is on
+    unsigned *next_k = cons_row + kNC;                                         // next chunk to hand out
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // equal contiguous share of the chunk list (32-bit: the launcher refuses tensors of more than 2^31 chunks)
@@ -583,16 +559,14 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     const unsigned cpr = (unsigned)p.chunks_per_row;
     const unsigned row_begin = c_begin / cpr;
     const AntqCodebook *__restrict__ cb = p.cb;
-    static_assert(kRT + kNC <= kThreads, "one thread per flag word at start-up");
+    static_assert(kRT + kNC + 1 <= kThreads, "one thread per flag word at start-up");
+    static_assert(kRing == 2, "each consumer warp double-buffers");
 
     if (warp == 0) ANTQS_TR(0);
     // Programmatic dependent launch: the next kernel in the stream may be scheduled onto SMs as our CTAs leave them ...
     asm volatile("griddepcontrol.launch_dependents;");
-    if (threadIdx.x < kNS) {
-        antq_mbar_init(full + threadIdx.x, 1);
-        antq_mbar_init(empty + threadIdx.x, kTeam);
-    }
-    if (threadIdx.x < kRT + kNC) built[threadIdx.x] = 0;                       // built[] and cons_row[] are contiguous
+    if (threadIdx.x < kNS) antq_mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x < kRT + kNC + 1) built[threadIdx.x] = 0;                   // built[], cons_row[], next_k are contiguous
     __syncthreads();
     // ... and everything above overlapped the tail of the previous kernel; nothing it may have written (x, alpha, the
     // codebook) or may still be reading (out) is touched before it has completed and flushed.
@@ -606,19 +580,26 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     const int ngroups = p.alpha_per_row ? (int)((row_last - row_begin) / G + 1) : 1;
     // Groups [0, n_pro) are built in the PROLOGUE by every warp except the issuer, one group each, all at once: the
     // consumers have nothing to do until the first chunk lands, and a builder warp that has to share its scheduler
-    // with three busy consumers is ~4x slower per pass than at start-up (profiles/r02_notes.md).  Later groups (a CTA
+    // with three busy consumers is ~4x slower per pass than at start-up (profiles/r01_notes.md).  Later groups (a CTA
     // with more than kRT rows) are made by the builder warps as the consumers free ring slots.
     const int n_pro = min(ngroups, min(GS, kNC + kNB));
-    auto build_group = [&](int g, bool tr) {
+    struct BuildIn { float alpha, tpos, tneg, lev; };
+    auto build_inputs = [&](int g) {                                  // the global loads of one build pass
         const int sub = lane % NTP, grp = lane / NTP;
         const int nt_real = p.nt_real;
         const float inf = __int_as_float(0x7f800000);
         unsigned r = row_begin + (unsigned)(g * G + grp);
         r = r > last_row ? last_row : r;
-        const float alpha = __ldg(p.alpha + (p.alpha_per_row ? r : 0));
-        const float tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
-        const float tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : tpos;
-        const float lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
+        BuildIn in;
+        in.alpha = __ldg(p.alpha + (p.alpha_per_row ? r : 0));
+        in.tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
+        in.tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : in.tpos;
+        in.lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
+        return in;
+    };
+    auto build_group = [&](int g, const BuildIn &in, bool tr) {
+        const int sub = lane % NTP, grp = lane / NTP;
+        const float alpha = in.alpha, tpos = in.tpos, tneg = in.tneg, lev = in.lev;
         if (tr) ANTQS_TR(3);
         RowTab tab;
         build_tables<T, NT, SYM, OVP>(tab, p, alpha, tpos, tneg, lev, sub, grp, tr);
@@ -639,68 +620,67 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
         if (lane == 0) antqs_st_release(built + (g % GS), (unsigned)(g / GS) + 1u);   // release: tables visible
         if (tr) ANTQS_TR(4);
     };
-    if (warp != kNC) {
-        const int br = warp < kNC ? warp : warp - 1;                  // rank among the warps that build
-        if (br < n_pro) build_group(br, br == 0);
-    }
-
-    if (warp == kNC) {
-        // ------------------------------ issuer ------------------------------
-        // Lane L owns stage L and the chunks L, L + stages, ... that pass through it.  Chunks go in flight (one TMA
-        // bulk copy each) in order, as soon as their stage is free, but never more than `window` at a time: requesting
-        // the whole ring at start-up makes every SM's FIRST chunk wait behind ~30 MB of other requests (measured,
-        // profiles/r02_notes.md); a window of a few chunks per SM already covers the HBM latency-bandwidth product.
-        const int ns = p.stages;
-        int k = lane;                                                 // this lane's next chunk
-        unsigned epar = 1, fpar = 0;                                  // a fresh barrier passes a parity-1 test
-        bool active = lane < ns && k < n;
-        bool inflight = false;                                        // issued, not yet seen landed
-        // pacing: at most one more chunk per `pace` cycles (only bites during the first microseconds, when every
-        // stage is free and there are no stores yet)
-        long long next_t = clock64();
-        int allowed = 0, issued = 0;
-        while (__any_sync(0xffffffffu, active)) {
-            if (inflight && antqs_mbar_test(full + lane, fpar)) inflight = false;
-            {
-                const long long now = __shfl_sync(0xffffffffu, clock64(), 0);
-                while (now >= next_t && allowed - issued < 64) { ++allowed; next_t += p.pace; }
+    // Chunk geometry and the TMA request of chunk k into stage `stage` (lane 0 of the owning consumer warp).
+    struct Geo { long long base; int nvec, tail; unsigned row; };
+    auto geo_of = [&](int k) {
+        Geo g;
+        const unsigned c = c_begin + (unsigned)k;
+        g.row = c / cpr;
+        const long long col0 = (long long)(c - g.row * cpr) * p.chunk_elems;
+        const long long remain = p.cols - col0;
+        const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+        g.nvec = n_el / VEC;
+        g.tail = n_el - g.nvec * VEC;
+        g.base = (long long)g.row * p.cols + col0;
+        return g;
+    };
+    auto request = [&](const Geo &g, int stage, int k) {
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)g.nvec * 16u;
+            if (bytes) {
+                antq_fence_proxy_async();          // this warp's LDS reads of the stage precede the async-proxy write
+                antq_bulk_g2s(antqs_smem + (size_t)stage * kChunkMax, reinterpret_cast<const T *>(p.x) + g.base, bytes,
+                              full + stage);
+            } else {
+                antqs_mbar_arrive(full + stage);
             }
-            int budget = p.window - __popc(__ballot_sync(0xffffffffu, inflight));
-            budget = min(budget, allowed - issued);
-            const int kmin = __reduce_min_sync(0xffffffffu, active ? k : 0x7fffffff);
-            const bool go = active && (k - kmin) < budget && antqs_mbar_test(empty + lane, epar);
-            if (go) {
-                const unsigned c = c_begin + (unsigned)k;
-                const unsigned row = c / cpr;
-                const long long col0 = (long long)(c - row * cpr) * p.chunk_elems;
-                const long long remain = p.cols - col0;
-                const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
-                const unsigned bytes = (unsigned)(n_el / VEC) * 16u;
-                // (no fence.proxy.async: the consumer's reads of this stage are ordered before this copy by its
-                //  release-arrive on `empty` and the acquire-test above, as in every TMA load pipeline)
-                if (bytes)
-                    antq_bulk_g2s(antqs_smem + (size_t)lane * kChunkMax,
-                                  reinterpret_cast<const T *>(p.x) + (long long)row * p.cols + col0, bytes, full + lane);
-                else
-                    antqs_mbar_arrive(full + lane);
 #ifdef ANTQS_TRACE
-                if (p.trace && k < kTraceChunks) p.trace[(size_t)blockIdx.x * kTraceStride + 8 + 4 * k] = antqs_now();
+            if (p.trace && k < kTraceChunks) p.trace[(size_t)blockIdx.x * kTraceStride + 8 + 4 * k] = antqs_now();
 #endif
-                inflight = true;
-                fpar = epar ^ 1u;                                      // parity of the phase just started on `full`
-                k += ns;
-                epar ^= 1u;
-                active = k < n;
-            }
-            const unsigned went = __ballot_sync(0xffffffffu, go);
-            issued += __popc(went);
-            if (!went) __nanosleep(32);
         }
-    } else if (warp > kNC) {
+    };
+    // Consumer w owns chunks w, w + kNC, ... and a private ring of kRing stages (w, w + kNC, ...): the chunk after the
+    // one being computed is always in flight, so an SM has kNC * (kRing - 1) * 8 KiB outstanding -- the HBM
+    // latency-bandwidth product -- and no more (requesting the whole ring at start-up makes every SM's FIRST chunk queue
+    // behind ~30 MB of other requests: profiles/r01_notes.md).  No issuer warp, no `empty` barriers: the warp that
+    // frees a stage is the one that refills it.
+    // Chunks are handed out by a shared counter at the moment a warp REQUESTS them (one ahead of the one it computes):
+    // rows with ties or out-of-window values cost more than others, and a CTA's chunk count rarely divides by kNC.
+    auto claim = [&]() {
+        int k = 0;
+        if (lane == 0) k = (int)atomicAdd(next_k, 1u);
+        return __shfl_sync(0xffffffffu, k, 0);
+    };
+    BuildIn pin;
+    pin.alpha = 0.0f; pin.tpos = 0.0f; pin.tneg = 0.0f; pin.lev = 0.0f;
+    if (warp < n_pro) pin = build_inputs(warp);    // small loads first: they would queue behind the bulk copies
+    Geo cur;
+    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.row = 0;
+    int k = n;
+    if (warp < kNC) {
+        k = claim();
+        if (k < n) {
+            cur = geo_of(k);
+            request(cur, warp, k);                 // first chunk in flight before the tables are made
+        }
+    }
+    if (warp < n_pro) build_group(warp, pin, warp == 0);   // consumers 0.., then the builders
+
+    if (warp >= kNC) {
         // ------------------------------ table builders ------------------------------
         // Builder b makes the tables of row groups n_pro + b, n_pro + b + kNB, ... (G rows per pass, one lane per
         // threshold) and stores them in the row-table ring; the builders run ahead of the consumers by up to kRT rows.
-        const int b = warp - kNC - 1;
+        const int b = warp - kNC;
         for (int g = n_pro + b; g < ngroups; g += kNB) {
             const int r0 = g * G;                                     // first CTA-local row of the group
             if (r0 + G > kRT) {
@@ -714,24 +694,22 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                     __nanosleep(200);
                 }
             }
-            build_group(g, false);
+            build_group(g, build_inputs(g), false);
         }
     } else {
         // ------------------------------ consumers ------------------------------
-        // The consumers form kTeams teams of kTeam warps (one warp per scheduler).  Team t owns chunks t, t + kTeams, ...
-        // in order, and every warp of the team takes a fixed share of each chunk (whole 64-vector blocks): the latency of
-        // a chunk -- and with it the tail after the last chunk has landed, and the idle time when chunks do not divide
-        // evenly among warps -- is kTeam times shorter than with one warp per chunk, with no shared work counter.
-        // stages % kTeams == 0, so a team meets every stage it uses in lap order and a parity wait cannot alias.
-        const int team = warp / kTeam, part = warp % kTeam;
-        constexpr int nparts = kTeam;
-        int stage = team;
-        unsigned parity = 0;
-        for (int k = team; k < n; k += kTeams, stage += kTeams) {
-            if (stage >= p.stages) { stage -= p.stages; parity ^= 1u; }
-            const unsigned c = c_begin + (unsigned)k;
-            const unsigned row = c / cpr;
-            const int idx = (int)(c - row * cpr);
+        int slot = 0;                                                  // which of this warp's two stages holds chunk k
+        unsigned phases = 0;                                           // bit r = parity to wait for on slot r
+        while (k < n) {
+            const int stage = warp + slot * kNC;
+            const Geo g = cur;
+            // the stage freed by the previous iteration takes the next chunk
+            const int kn = claim();
+            if (kn < n) {
+                cur = geo_of(kn);
+                request(cur, warp + (slot ^ 1) * kNC, kn);
+            }
+            const unsigned row = g.row;
             const unsigned rl = p.alpha_per_row ? row - row_begin : 0u;        // CTA-local row = table index
             if (lane == 0) antqs_st_release(cons_row + warp, rl);              // builders may recycle slots of rows < rl
             {
@@ -746,18 +724,14 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             const uint4 m1 = reinterpret_cast<const uint4 *>(tab + 7 * NTP)[1];
             const float s = __uint_as_float(m0.x);
             const uint32_t flags = m0.y, xlim = m0.z;
-            const long long col0 = (long long)idx * p.chunk_elems;
-            const long long remain = p.cols - col0;
-            const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
-            const int nvec = n_el / VEC, tail = n_el - nvec * VEC;
-            const long long base = (long long)row * p.cols + col0;
+            const int nvec = g.nvec, tail = g.tail;
+            const long long base = g.base;
             const uint4 *sv = reinterpret_cast<const uint4 *>(antqs_smem + (size_t)stage * kChunkMax);
             T *og = reinterpret_cast<T *>(p.out) + base;
-            antq_mbar_wait(full + stage, parity);                      // the chunk has landed in shared memory
+            antq_mbar_wait(full + stage, (phases >> slot) & 1u);       // the chunk has landed in shared memory
+            phases ^= 1u << slot;
             ANTQS_TRK(k, 2);
-            const int nblk = (nvec + 63) >> 6;
-            const int va = ((part * nblk) / nparts) << 6;
-            const int vb = min((((part + 1) * nblk) / nparts) << 6, nvec);
+            const int va = 0, vb = nvec;
             bool special = !(flags & kRowOk);
             if (vb > va && !special) {
                 uint4 *ov = reinterpret_cast<uint4 *>(og);
@@ -787,13 +761,14 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                 antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, va, vb, lane);
             }
             // ragged tail (only a per-tensor view can have one: rows == 1): straight from global memory
-            if (tail > 0 && lane == 0 && part == nparts - 1) {
+            if (tail > 0 && lane == 0) {
                 const T *xg = reinterpret_cast<const T *>(p.x) + base + (long long)nvec * VEC;
                 antqs_slow_vec<T, OVP>(cb, s, xg, og + (long long)nvec * VEC, tail);
             }
             __syncwarp();                                              // every lane is done with this stage
-            if (lane == 0) antqs_mbar_arrive(empty + stage);           // the stage is free once the whole team has arrived
             ANTQS_TRK(k, 3);
+            k = kn;
+            slot ^= 1;
         }
         if (lane == 0) antqs_st_release(cons_row + warp, 0xffffffffu);  // done: never holds a table slot again
 #ifdef ANTQS_TRACE
@@ -804,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
 
 template <typename T, int NT, bool SYM, bool OVP> int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_stream_kernel<T, NT, SYM, OVP>;
-    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + 2 * kNS * 8 + (kRT + kNC) * 4 + 16;
+    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + kNS * 8 + (kRT + kNC + 1) * 4 + 16;
     static bool configured = false;      // per instantiation; the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -861,17 +836,11 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
     const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
     const int es = dtype == ANTQ_F32 ? 4 : 2;
-    static int dbg = -1, chunk_env = 0, stages_env = 0, window_env = 0, pace_env = 0;
+    static int dbg = -1, chunk_env = 0;
     if (dbg < 0) {
         const char *e = getenv("ANTQ_DEBUG");
         const char *c = getenv("ANTQ_CHUNK");
-        const char *g = getenv("ANTQ_STAGES");
         chunk_env = c ? atoi(c) : 0;
-        stages_env = g ? atoi(g) : 0;
-        const char *w = getenv("ANTQ_WINDOW");
-        window_env = w ? atoi(w) : 0;
-        const char *pc = getenv("ANTQ_PACE");
-        pace_env = pc ? atoi(pc) : 0;
         dbg = e ? atoi(e) : 0;
     }
     StreamParams p;
@@ -901,9 +870,6 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     p.nt_real = nt; p.mid = info->mid; p.ovp_index = info->ovp_index; p.n_entries = info->n_entries;
     p.gmax = info->gmax; p.lim = info->lim;
     p.debug = dbg;
-    p.stages = (stages_env >= kTeams && stages_env <= kNS && stages_env % kTeams == 0) ? stages_env : kNS;
-    p.window = window_env >= 1 ? window_env : kWindow;
-    p.pace = pace_env >= 1 ? pace_env : kPace;
     p.trace = antqs_trace_buffer;
     const int ctas = (int)(p.total_chunks < (unsigned)kNumSms ? p.total_chunks : (unsigned)kNumSms);
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;

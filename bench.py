@@ -199,7 +199,7 @@ def main():
     xs = [x.to(device) for x in xs_h]
     alphas = [a.to(device) for a in alphas_h]
     outs = [torch.empty_like(x) for x in xs]
-    assert antq.fakequant_plan(xs[0], cb, True) == 1, "row-table kernel not selected"
+    assert antq.fakequant_plan(xs[0], cb, True) == 1, "row-table (stream) kernel not selected"
 
     def step():
         for i in range(NB):
@@ -297,12 +297,12 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": N, "cols": N, "tensors_per_step": NB,
                    "l2_policy": "8 distinct tensor pairs rotate (537 MB per step > 126 MB L2)",
-                   "launch": "step = one CUDA graph of 8 antq_rows_kernel launches",
+                   "launch": "step = one CUDA graph of 8 antq_stream_kernel launches (programmatic dependent launch edges)",
                    "parallelism": "independent tensors per rank, no collective" if world > 1 else "single GPU",
                    "pct_of_hbm_peak": round(100.0 * value / world / peak, 2)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES,
-                     "kernel": "antq_rows_kernel<__half,7,SYM,noOVP,nocodes>", "launch_us": round(launch_us, 3),
+                     "kernel": "antq_stream_kernel<__half,7,SYM,noOVP>", "launch_us": round(launch_us, 3),
                      "algorithmic_bytes_per_launch": N * N * BYTES_PER_ELEM, "peak_source": peak_src},
         "e2e": e2e, "gpu_launches": args.steps * NB, "clocks": clocks,
     }
