@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_PKG, "csrc", "libantq%s.so" % os.environ.get("ANTQ_LIB_S
 
 F32, F16, BF16 = 0, 1, 2
 FLAG_OVP, FLAG_FORCE_FLAT, FLAG_FORCE_ROWS = 1, 2, 4
-CB_WELLSEP, CB_STE_EXACT, CB_SYMMETRIC, CB_OVP_OK = 1, 2, 4, 8
+CB_WELLSEP, CB_STE_EXACT, CB_SYMMETRIC, CB_OVP_OK, CB_SYMX = 1, 2, 4, 8, 16
 EINVAL, ENOTSUP, EALIGN = -1, -2, -3
 MAX_GRID = 512
 CODE_NONE = -1
@@ -59,10 +59,12 @@ def _load():
     L.antq_host_destroy.argtypes = [vp]
     L.antq_host_destroy.restype = None
     L.antq_host_fakequant.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, ci, ci]
+    L.antq_host_fakequant_async.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, ci, ci]
+    L.antq_host_synchronize.argtypes = [vp]
     L.antq_host_last_launches.argtypes = [vp]
     for name in ("antq_codebook_prepare", "antq_codebook_info_get", "antq_lut_nearest", "antq_fakequant",
                  "antq_fakequant_plan", "antq_absmax", "antq_mse_sweep", "antq_host_create",
-                 "antq_host_fakequant", "antq_host_last_launches"):
+                 "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches"):
         getattr(L, name).restype = ci
     return L
 

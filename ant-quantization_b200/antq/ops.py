@@ -192,8 +192,10 @@ class HostPipeline:
         except Exception:
             pass
 
-    def fakequant(self, x, out, alpha, grid, per_row, outliers=None, ovp=False):
-        """x/out: CPU tensors (ideally pinned), alpha/grid/outliers: CPU fp32 tensors."""
+    def fakequant(self, x, out, alpha, grid, per_row, outliers=None, ovp=False, sync=True):
+        """x/out: CPU tensors (ideally pinned), alpha/grid/outliers: CPU fp32 tensors.
+        sync=False only enqueues the copies and kernels (antq_host_fakequant_async): `out` is complete after
+        synchronize(), and consecutive tensors overlap on the PCIe link."""
         for t in (x, out, alpha, grid):
             if t.is_cuda:
                 raise RuntimeError("HostPipeline takes host tensors")
@@ -201,10 +203,14 @@ class HostPipeline:
         a = alpha.detach().to(torch.float32).reshape(-1).contiguous()
         g = grid.detach().to(torch.float32).reshape(-1).contiguous()
         o = outliers.detach().to(torch.float32).reshape(-1).contiguous() if outliers is not None else None
-        check(lib.antq_host_fakequant(self._h, _ptr(x), _ptr(out), _ptr(a), int(bool(per_row)), rows, cols,
-                                      _dtype_code(x), _ptr(g), g.numel(), _ptr(o), 0 if o is None else o.numel(),
-                                      _lib.FLAG_OVP if ovp else 0), "antq_host_fakequant")
+        fn = lib.antq_host_fakequant if sync else lib.antq_host_fakequant_async
+        check(fn(self._h, _ptr(x), _ptr(out), _ptr(a), int(bool(per_row)), rows, cols,
+                 _dtype_code(x), _ptr(g), g.numel(), _ptr(o), 0 if o is None else o.numel(),
+                 _lib.FLAG_OVP if ovp else 0), "antq_host_fakequant")
         return out
+
+    def synchronize(self):
+        check(lib.antq_host_synchronize(self._h), "antq_host_synchronize")
 
     @property
     def last_launches(self):

@@ -70,7 +70,9 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     bool ok = info != nullptr;
     if (ok) {
         const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
-        const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+        // signed int-k grids run as "symmetric + one extra negative level" in the stream kernel (no code output)
+        const bool symx = !sym && (info->flags & ANTQ_CB_SYMX) && !ovp && !codes;
+        const int nt = (sym || symx) ? info->n_mag - 1 : info->n_levels - 1;
         const int vec = 16 / es;
         ok = (info->flags & ANTQ_CB_WELLSEP) && (info->flags & ANTQ_CB_STE_EXACT) && nt >= 1 && nt <= 31;
         ok = ok && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)codes % 16 == 0);
@@ -145,8 +147,9 @@ struct antq_host_ctx {
     void *d_out[8];
     AntqCodebook *cb;
     float *d_grid;          // ANTQ_MAX_GRID floats
-    float *d_alpha;
-    size_t alpha_cap;
+    float *d_alpha[8];      // per stage: the alpha slice of the chunk in flight on that stage
+    size_t alpha_cap[8];
+    int next_stage;         // stages are used round-robin ACROSS calls, so consecutive tensors overlap
     float h_grid[ANTQ_MAX_GRID];
     int h_k_normal, h_k_out;
     antq_codebook_info info;
@@ -183,15 +186,43 @@ void antq_host_destroy(antq_host_ctx *c) {
     }
     if (c->cb) cudaFree(c->cb);
     if (c->d_grid) cudaFree(c->d_grid);
-    if (c->d_alpha) cudaFree(c->d_alpha);
+    for (int i = 0; i < 8; i++)
+        if (c->d_alpha[i]) cudaFree(c->d_alpha[i]);
     delete c;
 }
 
 int antq_host_last_launches(const antq_host_ctx *c) { return c ? c->last_launches : 0; }
 
-int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, const float *alpha_host,
-                        int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
-                        int k_normal, const float *outliers_host, int k_out, int flags) {
+static int antq_host_alpha(antq_host_ctx *c, int stage, const float *alpha_host, size_t n, cudaStream_t st) {
+    if (c->alpha_cap[stage] < n) {
+        cudaError_t e = cudaStreamSynchronize(st);            // the old buffer may still be read by a kernel
+        if (e != cudaSuccess) return (int)e;
+        if (c->d_alpha[stage]) cudaFree(c->d_alpha[stage]);
+        c->d_alpha[stage] = nullptr; c->alpha_cap[stage] = 0;
+        size_t cap = n < 4096 ? 4096 : n;
+        e = cudaMalloc((void **)&c->d_alpha[stage], sizeof(float) * cap);
+        if (e != cudaSuccess) return (int)e;
+        c->alpha_cap[stage] = cap;
+    }
+    return (int)cudaMemcpyAsync(c->d_alpha[stage], alpha_host, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+}
+
+int antq_host_synchronize(antq_host_ctx *c) {
+    if (!c) return ANTQ_EINVAL;
+    int rc = 0;
+    for (int i = 0; i < c->n_stages; i++) {
+        cudaError_t e = cudaStreamSynchronize(c->st[i]);
+        if (e != cudaSuccess && rc == 0) rc = (int)e;
+    }
+    return rc;
+}
+
+// Enqueues H2D -> kernel -> D2H for every chunk of the tensor and returns; out_host is complete after
+// antq_host_synchronize().  Chunks of consecutive calls share the stage ring, so the copies of tensor i + 1
+// overlap the kernels and read-backs of tensor i (both PCIe directions stay busy across calls).
+int antq_host_fakequant_async(antq_host_ctx *c, const void *x_host, void *out_host, const float *alpha_host,
+                              int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
+                              int k_normal, const float *outliers_host, int k_out, int flags) {
     const int es = esize(dtype);
     if (!c || es == 0 || rows < 0 || cols < 0 || !alpha_host || !grid_host) return ANTQ_EINVAL;
     if (k_normal < 1 || k_out < 0 || k_normal + k_out > ANTQ_MAX_GRID || (k_out > 0 && !outliers_host))
@@ -201,43 +232,32 @@ int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, co
     if (!x_host || !out_host) return ANTQ_EINVAL;
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return (int)e;
-    cudaStream_t s0 = c->st[0];
 
-    // codebook: rebuild only when the grid changed
+    // codebook: rebuild only when the grid changed (then every stage must have finished with the old one)
     float g[ANTQ_MAX_GRID];
     memset(g, 0, sizeof(g));
     memcpy(g, grid_host, sizeof(float) * k_normal);
     if (k_out) memcpy(g + k_normal, outliers_host, sizeof(float) * k_out);
     if (c->h_k_normal != k_normal || c->h_k_out != k_out || memcmp(g, c->h_grid, sizeof(g)) != 0) {
+        int rc = antq_host_synchronize(c);
+        if (rc) return rc;
+        cudaStream_t s0 = c->st[0];
         e = cudaMemcpyAsync(c->d_grid, g, sizeof(g), cudaMemcpyHostToDevice, s0);
         if (e != cudaSuccess) return (int)e;
-        int rc = antq_launch_prepare(c->d_grid, k_normal, c->d_grid + k_normal, k_out, c->cb, s0);
+        rc = antq_launch_prepare(c->d_grid, k_normal, c->d_grid + k_normal, k_out, c->cb, s0);
         if (rc) return rc;
         c->last_launches++;
-        rc = antq_codebook_info_get(c->cb, &c->info, s0);
+        rc = antq_codebook_info_get(c->cb, &c->info, s0);      // synchronises s0: the codebook is visible to all stages
         if (rc) return rc;
         c->last_launches++;
         memcpy(c->h_grid, g, sizeof(g));
         c->h_k_normal = k_normal; c->h_k_out = k_out;
     }
-    // alpha
-    const size_t n_alpha = alpha_per_row ? (size_t)rows : 1;
-    if (c->alpha_cap < n_alpha) {
-        if (c->d_alpha) cudaFree(c->d_alpha);
-        c->d_alpha = nullptr; c->alpha_cap = 0;
-        e = cudaMalloc((void **)&c->d_alpha, sizeof(float) * n_alpha);
-        if (e != cudaSuccess) return (int)e;
-        c->alpha_cap = n_alpha;
-    }
-    e = cudaMemcpyAsync(c->d_alpha, alpha_host, sizeof(float) * n_alpha, cudaMemcpyHostToDevice, s0);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaStreamSynchronize(s0);       // alpha + codebook visible to every stage stream
-    if (e != cudaSuccess) return (int)e;
 
     const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
     const size_t row_bytes = (size_t)cols * es;
     int rc = 0;
-    int stage = 0;
+    int stage = c->next_stage;
     if (alpha_per_row && rows > 1) {
         if (row_bytes > c->chunk_bytes) return ANTQ_ENOTSUP;
         if (ovp && (cols & 1)) return ANTQ_ENOTSUP;     // pairs would straddle chunk boundaries
@@ -246,10 +266,12 @@ int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, co
             const int64_t nr = (rows - r0) < rpc ? (rows - r0) : rpc;
             const size_t bytes = (size_t)nr * row_bytes;
             cudaStream_t st = c->st[stage];
+            rc = antq_host_alpha(c, stage, alpha_host + r0, (size_t)nr, st);
+            if (rc) break;
             e = cudaMemcpyAsync(c->d_in[stage], (const char *)x_host + (size_t)r0 * row_bytes, bytes,
                                 cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { rc = (int)e; break; }
-            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha + r0, 1, nr, cols, dtype, c->cb,
+            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha[stage], 1, nr, cols, dtype, c->cb,
                                 &c->info, flags, st);
             if (rc) break;
             c->last_launches++;
@@ -265,11 +287,13 @@ int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, co
             const int64_t ne = (n - i0) < epc ? (n - i0) : epc;
             const size_t bytes = (size_t)ne * es;
             cudaStream_t st = c->st[stage];
+            rc = antq_host_alpha(c, stage, alpha_host, 1, st);
+            if (rc) break;
             e = cudaMemcpyAsync(c->d_in[stage], (const char *)x_host + (size_t)i0 * es, bytes, cudaMemcpyHostToDevice,
                                 st);
             if (e != cudaSuccess) { rc = (int)e; break; }
-            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha, 0, 1, ne, dtype, c->cb, &c->info,
-                                flags, st);
+            rc = antq_fakequant(c->d_in[stage], c->d_out[stage], nullptr, c->d_alpha[stage], 0, 1, ne, dtype, c->cb,
+                                &c->info, flags, st);
             if (rc) break;
             c->last_launches++;
             e = cudaMemcpyAsync((char *)out_host + (size_t)i0 * es, c->d_out[stage], bytes, cudaMemcpyDeviceToHost,
@@ -277,11 +301,17 @@ int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, co
             if (e != cudaSuccess) rc = (int)e;
         }
     }
-    for (int i = 0; i < c->n_stages; i++) {
-        e = cudaStreamSynchronize(c->st[i]);
-        if (e != cudaSuccess && rc == 0) rc = (int)e;
-    }
+    c->next_stage = stage;
     return rc;
+}
+
+int antq_host_fakequant(antq_host_ctx *c, const void *x_host, void *out_host, const float *alpha_host,
+                        int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
+                        int k_normal, const float *outliers_host, int k_out, int flags) {
+    int rc = antq_host_fakequant_async(c, x_host, out_host, alpha_host, alpha_per_row, rows, cols, dtype, grid_host,
+                                       k_normal, outliers_host, k_out, flags);
+    const int rs = c ? antq_host_synchronize(c) : 0;
+    return rc ? rc : rs;
 }
 
 }  // extern "C"

@@ -114,6 +114,11 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
                 if (lev[mid + k] != -lev[mid - k]) sym = false;
         }
         if (sym) flags |= ANTQ_CB_SYMMETRIC;
+        // symmetric except for ONE extra level at the negative end (signed int-k: -2^(k-1) .. 2^(k-1) - 1)?
+        bool symx = !sym && !(L & 1) && L >= 4 && lev[L >> 1] == 0.0f;
+        for (int k = 1; symx && k < (L >> 1); k++)
+            if (lev[(L >> 1) + k] != -lev[(L >> 1) - k]) symx = false;
+        if (symx) { flags |= ANTQ_CB_SYMX; mid = L >> 1; }
         // OVP: outliers are levels with |v| > 32 (O/antquant/quant_modules.py:314)
         int ovp_index = -1;
         bool ovp_ok = true;
@@ -133,8 +138,8 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
         cb->n_normal = k_normal;
         cb->n_levels = L;
         cb->flags = flags;
-        cb->n_mag = sym ? mid + 1 : 0;
-        cb->mid = sym ? mid : 0;
+        cb->n_mag = sym ? mid + 1 : (symx ? mid : 0);     // SYMX: magnitudes 0 .. mid-1 exist on both sides
+        cb->mid = (sym || symx) ? mid : 0;
         cb->ovp_index = ovp_index;
         cb->gmax = s_gmax;
         cb->vmax = vmax;
@@ -156,9 +161,9 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
     }
     // symmetric magnitude thresholds
     if (i < ANTQ_MAX_GRID / 2) {
-        int mid = L >> 1;
+        int mid = L >> 1;                 // index of the zero level for SYMMETRIC (L odd) and SYMX (L even) alike
         float tp = __int_as_float(0x7f800000), tn = tp;
-        if ((L & 1) && i < mid) {
+        if ((L & 1) ? i < mid : (L >= 4 && i < mid - 1)) {
             tp = thr[mid + i];
             // negative side: -m_{i+1} is chosen while d < thr[mid-i-1], i.e. -d >= nextup(-thr)
             float nt = -thr[mid - i - 1];

@@ -54,7 +54,7 @@ constexpr int kRing = ANTQS_RING;         // private ring stages per consumer wa
 constexpr int kNS = kNC * kRing;          // stages per CTA
 constexpr int kChunkMax = ANTQS_CHUNK;    // bytes of tensor per stage
 constexpr int kNumSms = 148;
-constexpr int kMetaWords = 8;
+constexpr int kMetaWords = 12;
 constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
 constexpr int kThreads = (kNC + kNB) * 32;       // consumers | builders
 constexpr int kRT = 32;                    // row-table ring slots (power of two)
@@ -200,6 +200,7 @@ template <typename V> __device__ __forceinline__ uint32_t antqs_u32(const V &v) 
 struct RowTab {
     uint32_t X, Xn, T2, B, C, D, Cn;        // this lane's entry of each table
     uint32_t s_bits, flags, xlim, S2, xovp, xovpn;   // uniform over the lanes of one row group
+    uint32_t Xe, Ee, De;                    // XNEG: the extra level at the negative end (x < Xe selects it)
 };
 
 //   X[i]   min{x in T : fl32(x / s) >= thr_i}   (x >= 0, or every x for an asymmetric codebook)
@@ -211,9 +212,9 @@ struct RowTab {
 //          m = sat((S|x|) * (1/(uS)) - P/u) is exactly 1.0 for |x| >= X and exactly 0.0 for |x| <= P, because the
 //          fused product-sum is <= 0 or >= 1 before its single rounding; D[i] = O[i+1] - O[i] must be exactly
 //          representable (checked), so q <- m*D + q reproduces O[rank] without rounding.
-template <typename T, int NT, bool SYM, bool OVP>
+template <typename T, int NT, bool SYM, bool OVP, bool XNEG>
 __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, float alpha, float tpos, float tneg,
-                                             float lev, int sub, int grp, bool tr) {
+                                             float lev, float thr_e, float lev_e, int sub, int grp, bool tr) {
     typedef AntqType<T> A;
     typedef TabGeom<NT> TG;
     constexpr int NTP = TG::NTP;
@@ -257,6 +258,18 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
     const float xl = __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);    // conservative window in x-space
     t.xlim = antqs_word<T>(A::from_f32_rz(xl));
     t.S2 = 0; t.B = 0; t.C = 0; t.D = 0; t.Cn = 0;
+    t.Xe = 0; t.Ee = 0; t.De = 0;
+    // XNEG (signed int-k): the level below -max_common is chosen iff d < thr_e, i.e. x < Xe; its output is
+    // RN(lev_e * s) = -Oe.  Every lane of the row group computes the same values.
+    T Xe_t = A::from_bits(0), Oe_t = A::from_bits(0);
+    if constexpr (XNEG) {
+        if (row_ok) {
+            if constexpr (sizeof(T) == 2) { T dummy; antqs_x_threshold16<T>(thr_e, thr_e, s, &Xe_t, &dummy); }
+            else Xe_t = antq_x_threshold_exact<T>(thr_e, s);
+            Oe_t = A::from_f32_rn(__fmul_rn(-lev_e, s));               // magnitude of the extra level
+        }
+        t.Xe = antqs_word<T>(Xe_t);
+    }
     {
         const int oi = p.ovp_index;
         const bool has = OVP && oi >= 0 && oi < NT;
@@ -274,6 +287,11 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         if (SYM && sub == 0) e |= 0x8000u;                            // marker: "level is not the zero level"
         if (sub == NT) e = o0;
         t.T2 = e | (e << 16);
+        if constexpr (XNEG) {
+            const uint32_t otop = __shfl_sync(kFull, ob, nt_real, NTP);      // output of the largest common magnitude
+            const uint32_t ee = otop ^ (uint32_t)A::bits(Oe_t);
+            t.Ee = ee | (ee << 16);
+        }
 
         // FMA-pipe twin
         bool ok = row_ok && NT <= 15 && (!ties || NT <= 7) && !(p.debug & 16);
@@ -305,6 +323,13 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         const float dex = __fsub_rn(o_next, A::to_f32(Ol));
         const T D = A::from_f32_rn(dex);
         if (sub < nt_real) ok = ok && (A::to_f32(D) == dex);
+        if constexpr (XNEG) {
+            const float otop = __shfl_sync(kFull, A::to_f32(Ol), nt_real, NTP);
+            const float de = __fsub_rn(A::to_f32(Oe_t), otop);
+            const T De_t = A::from_f32_rn(de);
+            ok = ok && (A::to_f32(De_t) == de) && isfinite(A::to_f32(Oe_t));
+            t.De = antqs_word<T>(De_t);
+        }
         const bool fma_ok = (__ballot_sync(kFull, ok) & gmask) == gmask;
         t.D = antqs_word<T>(sub < nt_real ? D : A::from_bits(0));
         t.B = antqs_word<T>(A::from_f32_rn(Bv));
@@ -315,6 +340,7 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         if (fma_ok) t.flags |= kRowFma;
     } else {
         t.T2 = __float_as_uint(Ol);
+        if constexpr (XNEG) t.Ee = __float_as_uint(-Oe_t);            // fp32: the signed output itself
     }
 }
 
@@ -341,7 +367,7 @@ enum { kModeAlu = 0, kModeTies = 1, kModeMix = 2, kModeTiesMix = 3 };
 //   kModeTies     row with representable ties (negative inputs use Xn), ALU pipe only
 //   kModeTiesMix  the same with FMA twins: negative inputs select C - 1 (one LOP3) and the compare / accumulate
 //                 run on the FMA pipe; one pair of four stays on the ALU pipe
-template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
+template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Chain16 {
     typedef typename Pack2<T>::v2 v2;
     static constexpr int NTP = NT + 1;
     static constexpr bool TIES = SYM && (MODE == kModeTies || MODE == kModeTiesMix);
@@ -352,11 +378,16 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
     uint32_t Bf[FMA ? NT + 1 : 1], Cf[FMA ? NT + 1 : 1], Df[FMA ? NT + 1 : 1];
     uint32_t Cn[(FMA && TIES) ? NT + 1 : 1];
     uint32_t S2, xovp, xovpn;
+    uint32_t Xe, Ee, De;                      // XNEG: extra level at the negative end
     v2 mx;                                    // running max of |x| (NaN-propagating)
 
     __device__ __forceinline__ void load(const uint32_t *tab, uint32_t s2, uint32_t xo, uint32_t xon) {
         load_words<NT + 1>(X, tab);
         load_words<NT + 1>(E, tab + 2 * NTP);
+        if constexpr (XNEG) {
+            const uint4 me = reinterpret_cast<const uint4 *>(tab + 7 * NTP)[2];
+            Xe = me.x; Ee = me.y; De = me.z;
+        }
         if constexpr (TIES) load_words<NT + 1>(Xn, tab + NTP);
         if constexpr (FMA) {
             load_words<NT + 1>(Bf, tab + 3 * NTP);
@@ -391,6 +422,7 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
             const uint32_t m = __hge2_mask(a2, Pack2<T>::from_u32(t));
             q ^= m & E[i];
         }
+        if (XNEG) q ^= __hlt2_mask(x2, Pack2<T>::from_u32(Xe)) & Ee;   // below the most negative common level
         if (SYM) q &= xb | 0x7fff7fffu;        // keep the marker bit (level != 0) only where x is negative
         if (OVP) q &= ~ovp_mask(a2, neg);
         return q;
@@ -412,6 +444,7 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
             const v2 m = __hfma2_sat(xs, Pack2<T>::from_u32(Bf[i]), Pack2<T>::from_u32(c));
             q = __hfma2(m, Pack2<T>::from_u32(Df[i]), q);
         }
+        if (XNEG) q = __hfma2(__hlt2(x2, Pack2<T>::from_u32(Xe)), Pack2<T>::from_u32(De), q);
         uint32_t qb;
         if (SYM) {
             // (+-1) * q + 0: restores the sign and leaves a zero level at +0
@@ -446,16 +479,20 @@ template <typename T, int NT, bool SYM, bool OVP, int MODE> struct Chain16 {
 };
 
 // fp32: one element per register; fp32 x-space resolves ties, so negatives always use Xn.
-template <int NT, bool SYM, bool OVP> struct Chain32 {
+template <int NT, bool SYM, bool OVP, bool XNEG> struct Chain32 {
     static constexpr int NTP = NT + 1;
     uint32_t X[NT + 1], Xn[SYM ? NT + 1 : 1], O[NT + 1];
-    uint32_t xovp, xovpn;
+    uint32_t xovp, xovpn, Xe, Oe;
     float mx;
 
     __device__ __forceinline__ void load(const uint32_t *tab, uint32_t, uint32_t xo, uint32_t xon) {
         load_words<NT + 1>(X, tab);
         if constexpr (SYM) load_words<NT + 1>(Xn, tab + NTP);
         load_words<NT + 1>(O, tab + 2 * NTP);
+        if constexpr (XNEG) {
+            const uint4 me = reinterpret_cast<const uint4 *>(tab + 7 * NTP)[2];
+            Xe = me.x; Oe = me.y;
+        }
         xovp = xo; xovpn = xon;
         mx = 0.0f;
     }
@@ -475,6 +512,7 @@ template <int NT, bool SYM, bool OVP> struct Chain32 {
             q = m ? __uint_as_float(O[i + 1]) : q;
         }
         if (SYM && m0) q = __uint_as_float(__float_as_uint(q) | (__float_as_uint(x) & 0x80000000u));
+        if (XNEG) q = x < __uint_as_float(Xe) ? __uint_as_float(Oe) : q;
         if (OVP) {
             if constexpr (SYM) outlier = a >= __uint_as_float(neg ? xovpn : xovp);
             else outlier = a >= __uint_as_float(xovp);
@@ -537,7 +575,7 @@ __device__ __forceinline__ void antqs_st_release(unsigned *p, unsigned v) {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(antq_smem_u32(p)), "r"(v) : "memory");
 }
 
-template <typename T, int NT, bool SYM, bool OVP>
+template <typename T, int NT, bool SYM, bool OVP, bool XNEG>
 __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamParams p) {
     typedef AntqType<T> A;
     typedef TabGeom<NT> TG;
@@ -583,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     // with three busy consumers is ~4x slower per pass than at start-up (profiles/r01_notes.md).  Later groups (a CTA
     // with more than kRT rows) are made by the builder warps as the consumers free ring slots.
     const int n_pro = min(ngroups, min(GS, kNC + kNB));
-    struct BuildIn { float alpha, tpos, tneg, lev; };
+    struct BuildIn { float alpha, tpos, tneg, lev, thr_e, lev_e; };
     auto build_inputs = [&](int g) {                                  // the global loads of one build pass
         const int sub = lane % NTP, grp = lane / NTP;
         const int nt_real = p.nt_real;
@@ -595,6 +633,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
         in.tpos = sub < nt_real ? (SYM ? cb->mag_tpos[sub] : cb->thr[sub]) : inf;
         in.tneg = (SYM && sub < nt_real) ? cb->mag_tneg[sub] : in.tpos;
         in.lev = sub <= nt_real ? (SYM ? cb->level[p.mid + sub] : cb->level[sub]) : 0.0f;
+        in.thr_e = XNEG ? cb->thr[0] : 0.0f;
+        in.lev_e = XNEG ? cb->level[0] : 0.0f;
         return in;
     };
     auto build_group = [&](int g, const BuildIn &in, bool tr) {
@@ -602,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
         const float alpha = in.alpha, tpos = in.tpos, tneg = in.tneg, lev = in.lev;
         if (tr) ANTQS_TR(3);
         RowTab tab;
-        build_tables<T, NT, SYM, OVP>(tab, p, alpha, tpos, tneg, lev, sub, grp, tr);
+        build_tables<T, NT, SYM, OVP, XNEG>(tab, p, alpha, tpos, tneg, lev, in.thr_e, in.lev_e, sub, grp, tr);
         uint32_t *st = reinterpret_cast<uint32_t *>(ring + (size_t)((g * G + grp) & (kRT - 1)) * kTabBytes);
         st[sub] = tab.X;
         st[NTP + sub] = tab.Xn;
@@ -615,6 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             uint4 *m = reinterpret_cast<uint4 *>(st + 7 * NTP);
             m[0] = make_uint4(tab.s_bits, tab.flags, tab.xlim, tab.S2);
             m[1] = make_uint4(tab.xovp, tab.xovpn, 0u, 0u);
+            m[2] = make_uint4(tab.Xe, tab.Ee, tab.De, 0u);
         }
         __syncwarp();
         if (lane == 0) antqs_st_release(built + (g % GS), (unsigned)(g / GS) + 1u);   // release: tables visible
@@ -662,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
         return __shfl_sync(0xffffffffu, k, 0);
     };
     BuildIn pin;
-    pin.alpha = 0.0f; pin.tpos = 0.0f; pin.tneg = 0.0f; pin.lev = 0.0f;
+    pin.alpha = 0.0f; pin.tpos = 0.0f; pin.tneg = 0.0f; pin.lev = 0.0f; pin.thr_e = 0.0f; pin.lev_e = 0.0f;
     if (warp < n_pro) pin = build_inputs(warp);    // small loads first: they would queue behind the bulk copies
     Geo cur;
     cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.row = 0;
@@ -737,20 +778,20 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                 uint4 *ov = reinterpret_cast<uint4 *>(og);
                 if constexpr (sizeof(T) == 2) {
                     if ((flags & kRowTies) && (flags & kRowFma)) {
-                        Chain16<T, NT, SYM, OVP, (SYM && NT <= 7 ? kModeTiesMix : kModeTies)> ch;
+                        Chain16<T, NT, SYM, OVP, XNEG, (SYM && NT <= 7 ? kModeTiesMix : kModeTies)> ch;
                         special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else if (flags & kRowTies) {
-                        Chain16<T, NT, SYM, OVP, kModeTies> ch;
+                        Chain16<T, NT, SYM, OVP, XNEG, kModeTies> ch;
                         special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else if (flags & kRowFma) {
-                        Chain16<T, NT, SYM, OVP, (NT <= 15 ? kModeMix : kModeAlu)> ch;
+                        Chain16<T, NT, SYM, OVP, XNEG, (NT <= 15 ? kModeMix : kModeAlu)> ch;
                         special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else {
-                        Chain16<T, NT, SYM, OVP, kModeAlu> ch;
+                        Chain16<T, NT, SYM, OVP, XNEG, kModeAlu> ch;
                         special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     }
                 } else {
-                    Chain32<NT, SYM, OVP> ch;
+                    Chain32<NT, SYM, OVP, XNEG> ch;
                     special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                 }
             }
@@ -777,8 +818,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     }
 }
 
-template <typename T, int NT, bool SYM, bool OVP> int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
-    auto kernel = antq_stream_kernel<T, NT, SYM, OVP>;
+template <typename T, int NT, bool SYM, bool OVP, bool XNEG = false>
+int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
+    auto kernel = antq_stream_kernel<T, NT, SYM, OVP, XNEG>;
     const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + kNS * 8 + (kRT + kNC + 1) * 4 + 16;
     static bool configured = false;      // per instantiation; the attribute is idempotent
     if (!configured) {
@@ -819,6 +861,19 @@ template <typename T, bool SYM, bool OVP> int launch_nt(const StreamParams &p, i
 #endif
 }
 
+// signed int-k: symmetric magnitudes plus one extra negative level
+template <typename T> int launch_symx(const StreamParams &p, int nt, int ctas, cudaStream_t st) {
+#ifndef ANTQS_DEV_ONLY_NT7
+    if (nt <= 3) return launch_kernel<T, 3, true, false, true>(p, ctas, st);
+#endif
+    if (nt <= 7) return launch_kernel<T, 7, true, false, true>(p, ctas, st);
+#ifndef ANTQS_DEV_ONLY_NT7
+    if (nt <= 15) return launch_kernel<T, 15, true, false, true>(p, ctas, st);
+    if (nt <= 31) return launch_kernel<T, 31, true, false, true>(p, ctas, st);
+#endif
+    return ANTQ_ENOTSUP;
+}
+
 template <typename T> int launch_t(const StreamParams &p, int nt, bool sym, bool ovp, int ctas, cudaStream_t st) {
     if (sym) return ovp ? launch_nt<T, true, true>(p, nt, ctas, st) : launch_nt<T, true, false>(p, nt, ctas, st);
     return ovp ? launch_nt<T, false, true>(p, nt, ctas, st) : launch_nt<T, false, false>(p, nt, ctas, st);
@@ -833,8 +888,9 @@ extern "C" void antq_debug_stream_trace(void *device_buffer) { antqs_trace_buffe
 // Returns ANTQ_ENOTSUP for configurations this kernel does not cover (the caller falls back to antq_rows_kernel).
 int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                        int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st) {
+    const bool symx = (info->flags & ANTQ_CB_SYMX) != 0 && !ovp && !(info->flags & ANTQ_CB_SYMMETRIC);
     const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
-    const int nt = sym ? info->n_mag - 1 : info->n_levels - 1;
+    const int nt = (sym || symx) ? info->n_mag - 1 : info->n_levels - 1;
     const int es = dtype == ANTQ_F32 ? 4 : 2;
     static int dbg = -1, chunk_env = 0;
     if (dbg < 0) {
@@ -874,6 +930,13 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     const int ctas = (int)(p.total_chunks < (unsigned)kNumSms ? p.total_chunks : (unsigned)kNumSms);
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
     p.chunks_rem = p.total_chunks % (unsigned)ctas;
+    if (symx) {
+        switch (dtype) {
+            case ANTQ_F32: return launch_symx<float>(p, nt, ctas, st);
+            case ANTQ_F16: return launch_symx<__half>(p, nt, ctas, st);
+            case ANTQ_BF16: return launch_symx<__nv_bfloat16>(p, nt, ctas, st);
+        }
+    }
     switch (dtype) {
         case ANTQ_F32: return launch_t<float>(p, nt, sym, ovp, ctas, st);
         case ANTQ_F16: return launch_t<__half>(p, nt, sym, ovp, ctas, st);

@@ -93,6 +93,8 @@ int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, 
 #define ANTQ_CB_STE_EXACT 2   /* (q - d) + d == q inside the window |d| <= lim */
 #define ANTQ_CB_SYMMETRIC 4   /* levels symmetric about a zero level */
 #define ANTQ_CB_OVP_OK    8   /* no outlier level (|v| > 32) on the negative side of an asymmetric grid */
+#define ANTQ_CB_SYMX     16   /* symmetric about zero except for one extra level at the negative end (signed int-k);
+                                 n_mag = magnitudes present on both sides, mid = index of the zero level */
 
 /* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
  * `info` (host pointer, may be NULL) lets the call pick the row-table kernel
@@ -125,6 +127,13 @@ void antq_host_destroy(antq_host_ctx *ctx);
 int antq_host_fakequant(antq_host_ctx *ctx, const void *x_host, void *out_host, const float *alpha_host,
                         int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
                         int k_normal, const float *outliers_host, int k_out, int flags);
+/* The same, without waiting: out_host is complete after antq_host_synchronize().  Consecutive calls share
+ * the stage ring, so both PCIe directions stay busy across tensors.  x_host, out_host (and a pinned
+ * alpha_host) must stay valid until then. */
+int antq_host_fakequant_async(antq_host_ctx *ctx, const void *x_host, void *out_host, const float *alpha_host,
+                              int alpha_per_row, int64_t rows, int64_t cols, int dtype, const float *grid_host,
+                              int k_normal, const float *outliers_host, int k_out, int flags);
+int antq_host_synchronize(antq_host_ctx *ctx);
 /* Kernels launched by the most recent antq_host_fakequant call. */
 int antq_host_last_launches(const antq_host_ctx *ctx);
 

@@ -40,6 +40,11 @@ def test_codebook_flags(antq):
         assert info["flags"] & _lib.CB_STE_EXACT, (kind, bit, signed, info)
         sym = bool(info["flags"] & _lib.CB_SYMMETRIC)
         assert sym == (signed and kind != "int"), (kind, bit, signed, info)
+        # signed int-k: symmetric magnitudes + one extra negative level, n_mag magnitudes on both sides
+        symx = bool(info["flags"] & _lib.CB_SYMX)
+        assert symx == (signed and kind == "int"), (kind, bit, signed, info)
+        if symx:
+            assert info["n_mag"] == 2 ** (bit - 1) and info["mid"] == 2 ** (bit - 1), info
         assert info["gmax"] == grid.max()
     for kind in ("int", "flint"):
         for signed in (True, False):
@@ -334,3 +339,74 @@ def test_errors_are_loud(antq):
         antq.fakequant(torch.zeros(4, 4, device=dev()), torch.ones(3, device=dev()), cb, True)
     z = antq.fakequant(torch.zeros(0, 4, device=dev()), torch.ones(0, device=dev()), cb, True)
     assert z.numel() == 0
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32", "bf16"])
+@pytest.mark.parametrize("bit", [3, 4, 5, 6])
+def test_stream_kernel_signed_int(antq, bit, dtype):
+    """Signed int-k runs as 'symmetric magnitudes + one extra negative level' in the stream kernel (6-bit only fits
+    the row-table kernels that way); values must equal the oracle and the generic flat kernel bit for bit."""
+    from antq import _lib
+    rng = np.random.default_rng(bit)
+    grid = orc.ant_grid("int", bit, True)
+    rows, cols = 200, 2048
+    x = (rng.standard_normal((rows, cols)) * 0.05).astype(np.float32)
+    x[rng.integers(0, rows, 30), rng.integers(0, cols, 30)] *= 40
+    alpha = (np.abs(x).max(1) * rng.uniform(0.3, 1.2, rows)).astype(np.float32)     # plenty of clipping at both ends
+    alpha[::9] = np.float32(0.05 * grid.max() / 8)                                   # representable ties
+    cb = _cb(antq, grid)
+    if dtype == "bf16":
+        xt = torch.from_numpy(x).to(torch.bfloat16)
+        ref = torch.from_numpy(orc.ant_forward(xt.float().numpy(), alpha, grid, per_row=True)).to(torch.bfloat16)
+        y = antq.fakequant(xt.to(dev()), torch.from_numpy(alpha).to(dev()), cb, True, flags=_lib.FLAG_FORCE_ROWS)
+        assert torch.equal(y.cpu().view(torch.int16), ref.view(torch.int16))
+        return
+    if dtype == "f16":
+        x = x.astype(np.float16)
+    ref = orc.ant_forward(x, alpha, grid, per_row=True)
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True) == 1
+    y = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_ROWS)
+    assert_bit_equal(y, ref, "signed int-%d %s" % (bit, dtype))
+    yt = _run_ant(antq, x.reshape(-1), np.float32(alpha.mean()), grid, False, _lib.FLAG_FORCE_ROWS)
+    assert_bit_equal(yt, orc.ant_forward(x.reshape(-1), np.float32(alpha.mean()), grid, per_row=False), "per-tensor")
+
+
+@pytest.mark.parametrize("rows,cols,dtype", [(148 * 45 + 7, 512, "f16"), (9000, 1032, "f16"), (5000, 520, "f32"),
+                                             (300, 10248, "f16"), (37, 512, "f16"), (3, 100000, "f16")])
+def test_stream_kernel_shapes(antq, rows, cols, dtype):
+    """Shapes that exercise the persistent kernel's bookkeeping: more than 32 rows per CTA (row-table ring reuse by
+    the builder warps), rows that are not a whole number of chunks, fewer chunks than SMs, very long rows."""
+    from antq import _lib
+    rng = np.random.default_rng(rows * 7 + cols)
+    grid = orc.ant_grid("flint", 4, True)
+    x = (rng.standard_normal((rows, cols)) * 0.05).astype(np.float32)
+    x[rng.integers(0, rows, 40), rng.integers(0, cols, 40)] *= 50           # out-of-window values -> cold fix-up pass
+    x[rows // 2, cols // 3] = np.nan
+    alpha = (np.abs(x).max(1) * rng.uniform(0.7, 1.3, rows)).astype(np.float32)
+    alpha[np.isnan(alpha)] = 0.1
+    alpha[::17] = np.float32(0.625 * 0.05)                                   # rows with representable ties
+    if dtype == "f16":
+        x = x.astype(np.float16)
+    ref = orc.ant_forward(x, alpha, grid, per_row=True)
+    y = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_ROWS)
+    assert_bit_equal(y, ref, "stream kernel %dx%d %s" % (rows, cols, dtype))
+    # in place
+    cb = _cb(antq, grid)
+    xd = torch.from_numpy(x).to(dev())
+    antq.fakequant(xd, torch.from_numpy(alpha).to(dev()), cb, True, out=xd, flags=_lib.FLAG_FORCE_ROWS)
+    assert_bit_equal(to_np(xd), ref, "in place")
+
+
+def test_stream_kernel_olive_many_rows(antq):
+    from antq import _lib
+    rng = np.random.default_rng(77)
+    grid, outl = orc.olive_grid("flint", 4, True), orc.olive_outlier_grid(4, True)
+    rows, cols = 148 * 40, 512
+    x = rng.standard_normal((rows, cols)).astype(np.float32)
+    idx = rng.integers(0, x.size, x.size // 150)
+    x.reshape(-1)[idx] *= rng.choice([8.0, 20.0, 60.0, 400.0], idx.size)
+    alpha = (3 * x.std(1) + np.abs(x.mean(1))).astype(np.float32)
+    x = x.astype(np.float16)
+    ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
+    y = _run_olive(antq, x, alpha, grid, outl, True, False, _lib.FLAG_FORCE_ROWS)
+    assert_bit_equal(y, ref, "olive many rows")
