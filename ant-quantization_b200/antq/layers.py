@@ -6,10 +6,14 @@ O/antquant/quant_modules.py:358-450, A/antquant/multihead_attention.py:486-687);
 matmul / conv itself stays a stock PyTorch op.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+CACHE_WEIGHTS = os.environ.get("ANTQ_CACHE_WEIGHTS", "1") != "0"
 
 
 def _copy_param(t):
@@ -36,8 +40,34 @@ def make_layers(TensorQuantizer):
             self.weight = _copy_param(src.weight)
             self.bias = _copy_param(getattr(src, "bias", None))
 
+        # Weight-quant cache: the reference re-fake-quantizes the weight on every forward
+        # (A/antquant/quant_modules.py:611-617); when nothing the result depends on has changed -- the weight, alpha,
+        # the grid (+ outliers), the enable flags -- and autograd is not recording, the previous result is returned:
+        # identical output, one launch and one pass over the weight less per forward.  `antq.layers.CACHE_WEIGHTS =
+        # False` (or ANTQ_CACHE_WEIGHTS=0) restores the reference's behaviour exactly.
+        def _weight_key(self):
+            q, w = self.quant_weight, self.weight
+            if not CACHE_WEIGHTS or not q._is_inited():
+                return None
+            if torch.is_grad_enabled() and (w.requires_grad or q.alpha.requires_grad) and q.flavor != "olive":
+                return None                                  # QAT: the fake-quant must stay on the autograd tape
+            o = getattr(q, "outliers", None)
+            return (w.data_ptr(), w._version, w.dtype, w.device, tuple(w.shape),
+                    q.alpha.data_ptr(), q.alpha._version, q.quant_grid.data_ptr(), q.quant_grid._version,
+                    None if o is None else (o.data_ptr(), o._version),
+                    q.mode, q.is_enable, q.is_enable_weight, bool(q.is_signed), q.is_perchannel)
+
         def _quantized(self, input):
-            weight = self.quant_weight(self.weight, input)
+            key = self._weight_key()
+            if key is not None and key == getattr(self, "_wq_key", None):
+                weight = self._wq_val
+            else:
+                weight = self.quant_weight(self.weight, input)
+                key = self._weight_key()                     # the first call calibrates: take the key afterwards
+                if key is not None and weight is not self.weight:
+                    self._wq_key, self._wq_val = key, weight.detach()
+                else:
+                    self._wq_key = self._wq_val = None
             input = self.quant_input(input, self.weight)
             return input, weight
 

@@ -188,3 +188,51 @@ def test_integration_md_ctypes_stub_runs():
     y = ns["fake_quant"](x.to(dev), alpha.to(dev), cb, info, True)
     ref = orc.ant_forward(x.numpy(), alpha.numpy(), grid, per_row=True)
     assert np.array_equal(y.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+
+
+@pytest.mark.parametrize("tree", ["ant", "olive"])
+def test_weight_quant_cache(tree):
+    """Eval-mode weight-quant cache of the layer wrappers: identical outputs with and without
+    it, a hit on the second forward, invalidation when the weight or alpha changes, never active under autograd."""
+    body = r'''
+import antq.layers as L
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+args = mkargs("ant-int-flint", w_up=150, a_up=150, w_low=75, a_low=75)
+lin = nn.Linear(512, 256).to(dev)
+q = LinearQuantizer(mode="ant-int-flint", wbit=4, abit=4, args=args)
+q.set_param(lin)
+q = q.to(dev)
+q.quant_weight.enable_quantization("w"); q.quant_input.enable_quantization("a")
+x = torch.randn(64, 512, device=dev)
+with torch.no_grad():
+    y0 = q(x)                                  # calibrates
+    y1 = q(x)
+    key1 = q._wq_key
+    y2 = q(x)
+    hit = q._wq_key is key1 and key1 is not None
+    L.CACHE_WEIGHTS = False
+    y_nocache = q(x)
+    L.CACHE_WEIGHTS = True
+    q.weight.mul_(1.5)                         # in-place change bumps the version: the cache must miss
+    y3 = q(x)
+    L.CACHE_WEIGHTS = False
+    y3_ref = q(x)
+    L.CACHE_WEIGHTS = True
+    q.quant_weight.alpha.data = q.quant_weight.alpha.data * 0.9
+    y4 = q(x)
+    L.CACHE_WEIGHTS = False
+    y4_ref = q(x)
+    L.CACHE_WEIGHTS = True
+grad_key = "n/a"
+if %(ant)s:
+    q.train()
+    yt = q(x)
+    grad_key = q._wq_key is None and yt.requires_grad
+RESULT.update(hit=bool(hit), same=bool(torch.equal(y1, y2) and torch.equal(y2, y_nocache)),
+              w_inval=bool(torch.equal(y3, y3_ref) and not torch.equal(y3, y2)),
+              a_inval=bool(torch.equal(y4, y4_ref) and not torch.equal(y4, y3)), grad=grad_key)
+''' % dict(ant="True" if tree == "ant" else "False")
+    res, _ = run(tree, body, timeout=600)
+    assert res["hit"] and res["same"] and res["w_inval"] and res["a_inval"], res
+    assert res["grad"] in (True, "n/a"), res
