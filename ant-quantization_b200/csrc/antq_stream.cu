@@ -411,7 +411,6 @@ template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Ch
         const v2 x2 = Pack2<T>::from_u32(xb);
         const v2 ab = __habs2(x2);
         const v2 a2 = SYM ? ab : x2;
-        mx = __hmax2_nan(mx, ab);
         uint32_t neg = 0;
         if (TIES) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));       // 0xffff where x < 0
         uint32_t q = SYM ? 0u : E[NT];
@@ -432,7 +431,6 @@ template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Ch
     __device__ __forceinline__ uint32_t pair_fma(uint32_t xb) {
         const v2 x2 = Pack2<T>::from_u32(xb);
         const v2 ab = __habs2(x2);
-        mx = __hmax2_nan(mx, ab);
         uint32_t neg = 0;
         if (TIES) neg = __hlt2_mask(x2, Pack2<T>::from_u32(0u));
         const v2 xs = __hmul2(SYM ? ab : x2, Pack2<T>::from_u32(S2));
@@ -459,6 +457,9 @@ template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Ch
 
     __device__ __forceinline__ uint4 vec(const uint4 r, int debug) {
         if (debug & 2) return r;
+        // running max of |x| over the vector: written as two back-to-back pairs so that ptxas emits 3-input VHMNMX
+        mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.x))), __habs2(Pack2<T>::from_u32(r.y)));
+        mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.z))), __habs2(Pack2<T>::from_u32(r.w)));
         uint4 q;
         q.x = pair_alu(r.x);
         if constexpr (MODE == kModeTiesMix) q.z = pair_fma(r.z);

@@ -410,3 +410,45 @@ def test_stream_kernel_olive_many_rows(antq):
     ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
     y = _run_olive(antq, x, alpha, grid, outl, True, False, _lib.FLAG_FORCE_ROWS)
     assert_bit_equal(y, ref, "olive many rows")
+
+
+def test_stream_kernel_dependent_launches(antq):
+    """Back-to-back launches whose input is the previous launch's output (programmatic dependent launch must not let
+    launch N+1 read before launch N has finished), out of place and in place, eager and inside a CUDA graph."""
+    rng = np.random.default_rng(3)
+    grids = [orc.ant_grid("flint", 4, True), orc.ant_grid("int", 4, True), orc.ant_grid("pot", 4, True)]
+    rows, cols = 2048, 4096
+    x = (rng.standard_normal((rows, cols)) * 0.05).astype(np.float16)
+    alphas = [(np.abs(x.astype(np.float32)).max(1) * r).astype(np.float32) for r in (1.0, 0.8, 0.6)]
+    ref = x
+    for g, a in zip(grids, alphas):
+        ref = orc.ant_forward(ref, a, g, per_row=True)
+    cbs = [_cb(antq, g) for g in grids]
+    ad = [torch.from_numpy(a).to(dev()) for a in alphas]
+    xd = torch.from_numpy(x).to(dev())
+
+    def chain(buf_in, bufs):
+        cur = buf_in
+        for cb, a, out in zip(cbs, ad, bufs):
+            antq.fakequant(cur, a, cb, True, out=out)
+            cur = out
+        return cur
+    for trial in range(5):
+        tmp = [torch.empty_like(xd) for _ in range(3)]
+        y = chain(xd, tmp)
+        assert_bit_equal(to_np(y), ref, "out-of-place chain, trial %d" % trial)
+        z = xd.clone()
+        y = chain(z, [z, z, z])
+        assert_bit_equal(to_np(y), ref, "in-place chain, trial %d" % trial)
+    tmp = [torch.empty_like(xd) for _ in range(3)]
+    chain(xd, tmp)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        chain(xd, tmp)
+    for t in tmp:
+        t.zero_()
+    gr.replay()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert_bit_equal(to_np(tmp[2]), ref, "graph replay")
