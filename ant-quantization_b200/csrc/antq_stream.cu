@@ -294,7 +294,8 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         }
 
         // FMA-pipe twin
-        bool ok = row_ok && NT <= 15 && (!ties || NT <= 7) && !(p.debug & 16);
+        bool ok = row_ok && NT <= 15 && (!ties || NT <= 7 || (OVP && NT == 15)) && !(p.debug & 16);   // (two-phase OVP runs
+        // its 7-threshold normal chain with the tie-aware FMA twin; the full 15-threshold chain never does)
         // S = 2^k with xlim * S in [2^13, 2^14): every in-window |x| stays finite after scaling
         int k = 13 - (int)((__float_as_uint(xl) >> 23) & 0xff) + 127;
         k = k > 15 ? 15 : (k < -14 ? -14 : k);
@@ -367,9 +368,9 @@ enum { kModeAlu = 0, kModeTies = 1, kModeMix = 2, kModeTiesMix = 3 };
 //   kModeTies     row with representable ties (negative inputs use Xn), ALU pipe only
 //   kModeTiesMix  the same with FMA twins: negative inputs select C - 1 (one LOP3) and the compare / accumulate
 //                 run on the FMA pipe; one pair of four stays on the ALU pipe
-template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Chain16 {
+template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE, int PITCH = NT + 1> struct Chain16 {
     typedef typename Pack2<T>::v2 v2;
-    static constexpr int NTP = NT + 1;
+    static constexpr int NTP = PITCH;         // table pitch of the row-table slot (> NT + 1 for a prefix chain)
     static constexpr bool TIES = SYM && (MODE == kModeTies || MODE == kModeTiesMix);
     static constexpr bool FMA = MODE == kModeMix || MODE == kModeTiesMix;
     uint32_t X[NT + 1];                       // [NT] unused
@@ -455,11 +456,18 @@ template <typename T, int NT, bool SYM, bool OVP, bool XNEG, int MODE> struct Ch
         return qb;
     }
 
-    __device__ __forceinline__ uint4 vec(const uint4 r, int debug) {
+    // max |x| of one vector (NaN-propagating)
+    __device__ static __forceinline__ v2 vec_max(const uint4 r) {
+        const v2 a = __hmax2_nan(__habs2(Pack2<T>::from_u32(r.x)), __habs2(Pack2<T>::from_u32(r.y)));
+        return __hmax2_nan(__hmax2_nan(a, __habs2(Pack2<T>::from_u32(r.z))), __habs2(Pack2<T>::from_u32(r.w)));
+    }
+    template <bool MAX = true> __device__ __forceinline__ uint4 vec(const uint4 r, int debug) {
         if (debug & 2) return r;
-        // running max of |x| over the vector: written as two back-to-back pairs so that ptxas emits 3-input VHMNMX
-        mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.x))), __habs2(Pack2<T>::from_u32(r.y)));
-        mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.z))), __habs2(Pack2<T>::from_u32(r.w)));
+        if constexpr (MAX) {
+            // running max of |x|: written as two back-to-back pairs so that ptxas emits 3-input VHMNMX
+            mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.x))), __habs2(Pack2<T>::from_u32(r.y)));
+            mx = __hmax2_nan(__hmax2_nan(mx, __habs2(Pack2<T>::from_u32(r.z))), __habs2(Pack2<T>::from_u32(r.w)));
+        }
         uint4 q;
         q.x = pair_alu(r.x);
         if constexpr (MODE == kModeTiesMix) q.z = pair_fma(r.z);
@@ -567,6 +575,78 @@ __device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uin
     return ch.special(xlim);
 }
 
+// OliVe, signed 4-bit (7 normal + 7 outlier thresholds on |x|), 16-bit types.  Outliers are rare (|x| beyond ~3 sigma),
+// but a 14-threshold chain + pair masking for every element costs twice the normal chain.  Two phases instead:
+//   1. every vector runs the 7-threshold NORMAL chain (exactly the ANT flint/int path; no pair can be masked if no
+//      element of the vector is an outlier) and remembers whether its max |x| reaches the first outlier threshold;
+//   2. the few vectors that hold an outlier are compacted into a per-warp list in shared memory and redone -- densely,
+//      one vector per lane -- with the full 14-threshold chain and the outlier-victim mask, from the staged copy.
+template <typename T, int MODE1, bool TIES2>
+__device__ __forceinline__ bool run_chunk_ovp2(const uint32_t *tab, const uint4 *sv, uint4 *og, int nvec, int lane,
+                                               uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim,
+                                               unsigned char *list, int debug) {
+    typedef typename Pack2<T>::v2 v2;
+    Chain16<T, 7, true, false, false, MODE1, 16> c1;
+    c1.load(tab, s2, xo, xon);
+    c1.E[7] = 0u;                                                   // slot 7 of the 16-pitch table is E[7], not O[0] = 0
+    const v2 xo2 = Pack2<T>::from_u32(xo);                          // positive-side threshold: <= the negative-side one
+    uint32_t pend = 0;                                              // bit j: vector j * 32 + lane holds an outlier
+    const uint4 *sp = sv + lane;
+    uint4 *op = og + lane;
+    const int nfull = nvec >> 6;
+#pragma unroll 1
+    for (int it = 0; it < nfull; ++it) {
+        const uint4 r0 = sp[0], r1 = sp[32];
+        const v2 m0 = c1.vec_max(r0), m1 = c1.vec_max(r1);
+        c1.mx = __hmax2_nan(__hmax2_nan(c1.mx, m0), m1);
+        const uint4 q0 = c1.template vec<false>(r0, debug);
+        const uint4 q1 = c1.template vec<false>(r1, debug);
+        if (__hge2_mask(m0, xo2)) pend |= 1u << (2 * it);
+        if (__hge2_mask(m1, xo2)) pend |= 2u << (2 * it);
+        antq_stg_stream(op, q0);
+        antq_stg_stream(op + 32, q1);
+        sp += 64; op += 64;
+    }
+#pragma unroll 1
+    for (int v = (nfull << 6) + lane; v < nvec; v += 32) {
+        const uint4 r0 = *sp;
+        const v2 m0 = c1.vec_max(r0);
+        c1.mx = __hmax2_nan(c1.mx, m0);
+        const uint4 q0 = c1.template vec<false>(r0, debug);
+        if (__hge2_mask(m0, xo2)) pend |= 1u << (v >> 5);
+        antq_stg_stream(op, q0);
+        sp += 32; op += 32;
+    }
+    const bool special = c1.special(xlim);
+    if (__any_sync(0xffffffffu, pend != 0) && !(debug & 2)) {
+        // compact the flagged vectors of the warp into `list` (index < 256 fits a byte)
+        const int cnt = __popc(pend);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = incl - cnt;
+        while (pend) {
+            const int j = __ffs(pend) - 1;
+            pend &= pend - 1;
+            list[pos++] = (unsigned char)(j * 32 + lane);
+        }
+        __syncwarp();          // the list is complete; phase-1 stores to these vectors are ordered before the rewrites
+        Chain16<T, 15, true, true, false, TIES2 ? kModeTies : kModeAlu> c2;
+        c2.load(tab, s2, xo, xon);
+#pragma unroll 1
+        for (int i = lane; i < total; i += 32) {
+            const int v = list[i];
+            antq_stg_stream(og + v, c2.template vec<false>(sv[v], debug));
+        }
+        __syncwarp();          // the list may be rewritten by this warp's next chunk
+    }
+    return special;
+}
+
 __device__ __forceinline__ unsigned antqs_ld_acquire(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(antq_smem_u32(p)) : "memory");
@@ -590,6 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     unsigned *built = reinterpret_cast<unsigned *>(full + kNS);               // [kRT] lap + 1 of the group in each ring slot
     unsigned *cons_row = built + kRT;                                          // [kNC] CTA-local row each consumer is on
     unsigned *next_k = cons_row + kNC;                                         // next chunk to hand out
+    unsigned char *ovp_list = reinterpret_cast<unsigned char *>(next_k + 4);   // [kNC][256] two-phase OVP work lists
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // equal contiguous share of the chunk list (32-bit: the launcher refuses tensors of more than 2^31 chunks)
@@ -777,7 +858,24 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             bool special = !(flags & kRowOk);
             if (vb > va && !special) {
                 uint4 *ov = reinterpret_cast<uint4 *>(og);
-                if constexpr (sizeof(T) == 2) {
+                bool done = false;
+                if constexpr (sizeof(T) == 2 && OVP && SYM && NT == 15) {
+                    if (p.ovp_index == 7 && va == 0 && !(p.debug & 128)) {
+                        // signed 4-bit OliVe: normal chain for everything, full chain only for the vectors with an outlier
+                        unsigned char *list = ovp_list + warp * 256;
+                        if ((flags & kRowTies) && (flags & kRowFma))
+                            special = run_chunk_ovp2<T, kModeTiesMix, true>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        else if (flags & kRowTies)
+                            special = run_chunk_ovp2<T, kModeTies, true>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        else if (flags & kRowFma)
+                            special = run_chunk_ovp2<T, kModeMix, false>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        else
+                            special = run_chunk_ovp2<T, kModeAlu, false>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        done = true;
+                    }
+                }
+                if (done) {
+                } else if constexpr (sizeof(T) == 2) {
                     if ((flags & kRowTies) && (flags & kRowFma)) {
                         Chain16<T, NT, SYM, OVP, XNEG, (SYM && NT <= 7 ? kModeTiesMix : kModeTies)> ch;
                         special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
@@ -822,7 +920,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
 template <typename T, int NT, bool SYM, bool OVP, bool XNEG = false>
 int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_stream_kernel<T, NT, SYM, OVP, XNEG>;
-    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + kNS * 8 + (kRT + kNC + 1) * 4 + 16;
+    const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + kNS * 8 + (kRT + kNC + 4) * 4 + kNC * 256 + 16;
     static bool configured = false;      // per instantiation; the attribute is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
