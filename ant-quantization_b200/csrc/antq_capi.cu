@@ -12,6 +12,9 @@ int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alph
                      cudaStream_t st);
 int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                        int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
+int antq_launch_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                      int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
+int antq_short_thresholds(const antq_codebook_info *info, bool ovp);
 int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
 int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
@@ -29,7 +32,7 @@ extern "C" {
 int antq_abi_version(void) { return ANTQ_ABI_VERSION; }
 
 const char *antq_build_info(void) {
-    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
+    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_short_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
            "antq_mse_sweep_kernel; built " __DATE__;
 }
 
@@ -81,7 +84,13 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
         ok = ok && (cols >= kRowsMinCols || (flags & ANTQ_FLAG_FORCE_ROWS));
     }
     if (ok) return 1;
-    return (flags & ANTQ_FLAG_FORCE_ROWS) ? ANTQ_ENOTSUP : 2;
+    if (flags & ANTQ_FLAG_FORCE_ROWS) return ANTQ_ENOTSUP;
+    // short rows / scale groups: the d-space chain kernel (no code output, <= 15 thresholds after folding signs)
+    if (info && !codes && (info->flags & ANTQ_CB_WELLSEP) && rows > 1 && cols < kRowsMinCols && cols % (16 / es) == 0 &&
+        ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && antq_short_thresholds(info, ovp) >= 1 &&
+        antq_short_thresholds(info, ovp) <= 15 && (!ovp || (info->flags & ANTQ_CB_OVP_OK)))
+        return 3;
+    return 2;
 }
 
 int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, int64_t rows,
@@ -108,6 +117,11 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
         }
         return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
                                 (cudaStream_t)stream);
+    }
+    if (plan == 3) {
+        const int rc = antq_launch_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
+                                         (cudaStream_t)stream);
+        if (rc != ANTQ_ENOTSUP) return rc;
     }
     return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp,
                             (cudaStream_t)stream);

@@ -104,7 +104,9 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
                    const antq_codebook_info *info, int flags, void *stream);
 
 /* Which kernel antq_fakequant launches for these arguments:
- * 1 = row-table kernel (x-space thresholds), 2 = flat generic kernel, <0 = error. */
+ * 1 = row-table kernels (x-space thresholds: antq_stream_kernel, antq_rows_kernel when codes are requested),
+ * 3 = short-row / scale-group kernel (d-space threshold chain, rows shorter than 512 elements),
+ * 2 = flat generic kernel, <0 = error. */
 int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t cols, int dtype, int flags,
                         const void *x, const void *out, const void *codes);
 

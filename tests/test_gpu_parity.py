@@ -452,3 +452,54 @@ def test_stream_kernel_dependent_launches(antq):
     gr.replay()
     torch.cuda.synchronize()
     assert_bit_equal(to_np(tmp[2]), ref, "graph replay")
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("kind,bit,signed,cols", [("flint", 4, True, 32), ("int", 4, True, 16), ("pot", 4, True, 8),
+                                                  ("flint", 4, False, 64), ("int", 4, False, 256), ("float2", 4, True, 128),
+                                                  ("int", 5, True, 32), ("flint", 3, True, 504), ("int", 3, False, 40)])
+def test_short_rows_and_scale_groups(antq, kind, bit, signed, cols, dtype):
+    """Rows shorter than 512 elements (group-8/16/32 scales, 1x1-conv weights) take antq_short_kernel (plan 3):
+    bit-exact against the oracle and the generic flat kernel, including clipped / NaN / Inf inputs and dead rows."""
+    from antq import _lib
+    rng = np.random.default_rng(cols * 31 + bit)
+    grid = orc.ant_grid(kind, bit, signed)
+    rows = 70000 // cols * 8
+    x = (rng.standard_normal((rows, cols)) * 0.05).astype(np.float32)
+    x[rng.integers(0, rows, 60), rng.integers(0, cols, 60)] *= 500          # far outside the window
+    x[7, 3], x[11, 5], x[13, cols - 1] = np.nan, np.inf, -np.inf
+    x[20] = 0.0                                                            # alpha = 0 row
+    if not signed:
+        x = np.abs(x)
+    alpha = (np.abs(np.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)).max(1) * rng.uniform(0.4, 1.2, rows)).astype(np.float32)
+    alpha[::5] = np.float32(0.05 * grid.max() / 8)                           # representable ties
+    if dtype == "f16":
+        x = x.astype(np.float16)
+    cb = _cb(antq, grid)
+    xd = torch.from_numpy(x).to(dev())
+    assert antq.fakequant_plan(xd, cb, True) == 3
+    ref = orc.ant_forward(x, alpha, grid, per_row=True)
+    y = _run_ant(antq, x, alpha, grid, True, 0)
+    assert_bit_equal(y, ref, "short kernel %s-%d cols=%d %s" % (kind, bit, cols, dtype))
+    yf = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_FLAT)
+    assert_bit_equal(yf, ref, "flat kernel")
+    antq.fakequant(xd, torch.from_numpy(alpha).to(dev()), cb, True, out=xd)
+    assert_bit_equal(to_np(xd), ref, "in place")
+
+
+@pytest.mark.parametrize("kind,signed", [("flint", True), ("int", True)])
+def test_short_rows_olive(antq, kind, signed):
+    rng = np.random.default_rng(9)
+    grid, outl = orc.olive_grid(kind, 4, signed), orc.olive_outlier_grid(4, signed)
+    rows, cols = 4096, 64
+    x = rng.standard_normal((rows, cols)).astype(np.float32)
+    idx = rng.integers(0, x.size, x.size // 100)
+    x.reshape(-1)[idx] *= rng.choice([8.0, 20.0, 60.0, 400.0], idx.size)
+    x.reshape(-1)[idx[:80] ^ 1] *= 30.0
+    alpha = (3 * x.std(1) + np.abs(x.mean(1))).astype(np.float32)
+    x = x.astype(np.float16)
+    cb = _cb(antq, grid, outl)
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True, ovp=True) == 3
+    ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
+    y = _run_olive(antq, x, alpha, grid, outl, True, False, 0)
+    assert_bit_equal(y, ref, "olive short rows")
