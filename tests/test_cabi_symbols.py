@@ -34,7 +34,9 @@ def test_abi_basics_without_gpu():
     assert _lib.lib.antq_codebook_prepare(None, 0, None, 0, None, None) == _lib.EINVAL
     info = _lib.CodebookInfo(n_entries=16, n_normal=16, n_levels=15, flags=7, n_mag=8, mid=7, ovp_index=-1)
     assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 4096, _lib.F16, 0, 256, 512, None) == 1
-    assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 64, _lib.F16, 0, 256, 512, None) == 2
+    assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 64, _lib.F16, 0, 256, 512, None) == 3    # short rows
+    assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 64, _lib.F16, 0, 256, 512, 1024) == 2  # codes wanted
+    assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 61, _lib.F16, 0, 256, 512, None) == 2  # ragged rows
     assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 4097, _lib.F16, _lib.FLAG_FORCE_ROWS, 256, 512,
                                         None) == _lib.ENOTSUP
     assert _lib.lib.antq_fakequant_plan(None, 4096, 4096, _lib.F16, 0, 256, 512, None) == 2
