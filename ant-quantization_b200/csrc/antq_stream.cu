@@ -57,13 +57,14 @@ constexpr int kNumSms = 148;
 constexpr int kMetaWords = 12;
 constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
 constexpr int kThreads = (kNC + kNB) * 32;       // consumers | builders
+static_assert(kChunkMax <= 4096, "two-phase OVP keeps vector indices of a chunk in one byte");
 constexpr int kRT = 32;                    // row-table ring slots (power of two)
 
 enum : uint32_t { kRowOk = 1u, kRowTies = 2u, kRowFma = 4u };
 
 template <int NT> struct TabGeom {
     static constexpr int NTP = NT + 1;                 // table pitch in words: 4, 8, 16, 32
-    static constexpr int G = 32 / NTP;                 // rows built at once by the producer warp
+    static constexpr int G = 32 / NTP;                 // rows built in one pass of a warp
     static constexpr int kTabBytes = ((7 * NTP + kMetaWords) * 4 + 127) / 128 * 128;
 };
 
@@ -77,7 +78,7 @@ struct StreamParams {
     int alpha_per_row, chunks_per_row, chunk_elems;
     int nt_real, mid, ovp_index, n_entries;
     float gmax, lim;
-    int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin
+    int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin, 128 = one-phase OVP
     unsigned long long *trace;   // ANTQS_TRACE builds: per-CTA timeline (tools/trace_stream.py)
 };
 
@@ -131,10 +132,10 @@ __device__ __noinline__ void antqs_slow_vec(const AntqCodebook *__restrict__ cb,
 // element (or every vector, when the row's scale is not a positive finite number) is recomputed.
 template <typename T, bool OVP>
 __device__ __noinline__ void antqs_fixup_chunk(const AntqCodebook *__restrict__ cb, float s, float xlim, bool all,
-                                               const uint4 *sv, T *og, int va, int nvec, int lane) {
+                                               const uint4 *sv, T *og, int nvec, int lane) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
-    for (int v = va + lane; v < nvec; v += 32) {
+    for (int v = lane; v < nvec; v += 32) {
         const T *xv = reinterpret_cast<const T *>(sv + v);
         bool special = all;
 #pragma unroll
@@ -550,13 +551,12 @@ template <int NT, bool SYM, bool OVP, bool XNEG> struct Chain32 {
 
 // One chunk from shared memory to global memory: two vectors per lane per iteration, then the remainder.
 template <typename CH>
-__device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uint4 *sv, uint4 *og, int va, int nvec,
-                                          int lane, uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim, int debug) {
-    // vectors [va, nvec) of the chunk (this warp's part)
+__device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uint4 *sv, uint4 *og, int nvec, int lane,
+                                          uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim, int debug) {
     ch.load(tab, s2, xo, xon);
-    const uint4 *sp = sv + va + lane;
-    uint4 *op = og + va + lane;
-    const int nfull = (nvec - va) >> 6;
+    const uint4 *sp = sv + lane;
+    uint4 *op = og + lane;
+    const int nfull = nvec >> 6;
 #pragma unroll 1
     for (int it = 0; it < nfull; ++it) {
         const uint4 r0 = sp[0], r1 = sp[32];                   // LDS.128, conflict free
@@ -567,7 +567,7 @@ __device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uin
         sp += 64; op += 64;
     }
 #pragma unroll 1
-    for (int v = va + (nfull << 6) + lane; v < nvec; v += 32) {
+    for (int v = (nfull << 6) + lane; v < nvec; v += 32) {
         const uint4 q0 = ch.vec(*sp, debug);
         antq_stg_stream(op, q0);
         sp += 32; op += 32;
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     const unsigned last_row = (unsigned)(p.rows - 1);
     const unsigned row_last = (c_begin + (unsigned)n - 1u) / cpr;
     const int ngroups = p.alpha_per_row ? (int)((row_last - row_begin) / G + 1) : 1;
-    // Groups [0, n_pro) are built in the PROLOGUE by every warp except the issuer, one group each, all at once: the
+    // Groups [0, n_pro) are built in the PROLOGUE, one group per warp, all at once: the
     // consumers have nothing to do until the first chunk lands, and a builder warp that has to share its scheduler
     // with three busy consumers is ~4x slower per pass than at start-up (profiles/r01_notes.md).  Later groups (a CTA
     // with more than kRT rows) are made by the builder warps as the consumers free ring slots.
@@ -854,23 +854,22 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             antq_mbar_wait(full + stage, (phases >> slot) & 1u);       // the chunk has landed in shared memory
             phases ^= 1u << slot;
             ANTQS_TRK(k, 2);
-            const int va = 0, vb = nvec;
             bool special = !(flags & kRowOk);
-            if (vb > va && !special) {
+            if (nvec > 0 && !special) {
                 uint4 *ov = reinterpret_cast<uint4 *>(og);
                 bool done = false;
                 if constexpr (sizeof(T) == 2 && OVP && SYM && NT == 15) {
-                    if (p.ovp_index == 7 && va == 0 && !(p.debug & 128)) {
+                    if (p.ovp_index == 7 && !(p.debug & 128)) {
                         // signed 4-bit OliVe: normal chain for everything, full chain only for the vectors with an outlier
                         unsigned char *list = ovp_list + warp * 256;
                         if ((flags & kRowTies) && (flags & kRowFma))
-                            special = run_chunk_ovp2<T, kModeTiesMix, true>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, kModeTiesMix, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else if (flags & kRowTies)
-                            special = run_chunk_ovp2<T, kModeTies, true>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, kModeTies, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else if (flags & kRowFma)
-                            special = run_chunk_ovp2<T, kModeMix, false>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, kModeMix, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else
-                            special = run_chunk_ovp2<T, kModeAlu, false>(tab, sv, ov, vb, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, kModeAlu, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         done = true;
                     }
                 }
@@ -878,27 +877,27 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                 } else if constexpr (sizeof(T) == 2) {
                     if ((flags & kRowTies) && (flags & kRowFma)) {
                         Chain16<T, NT, SYM, OVP, XNEG, (SYM && NT <= 7 ? kModeTiesMix : kModeTies)> ch;
-                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else if (flags & kRowTies) {
                         Chain16<T, NT, SYM, OVP, XNEG, kModeTies> ch;
-                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else if (flags & kRowFma) {
                         Chain16<T, NT, SYM, OVP, XNEG, (NT <= 15 ? kModeMix : kModeAlu)> ch;
-                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     } else {
                         Chain16<T, NT, SYM, OVP, XNEG, kModeAlu> ch;
-                        special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                        special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                     }
                 } else {
                     Chain32<NT, SYM, OVP, XNEG> ch;
-                    special = run_chunk(ch, tab, sv, ov, va, vb, lane, m0.w, m1.x, m1.y, xlim, p.debug);
+                    special = run_chunk(ch, tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, p.debug);
                 }
             }
-            if (vb > va && __any_sync(0xffffffffu, special)) {
+            if (nvec > 0 && __any_sync(0xffffffffu, special)) {
                 float xl;
                 if constexpr (sizeof(T) == 2) xl = A::to_f32(A::from_bits((typename A::bits_t)(xlim & 0xffffu)));
                 else xl = __uint_as_float(xlim);
-                antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, va, vb, lane);
+                antqs_fixup_chunk<T, OVP>(cb, s, xl, !(flags & kRowOk), sv, og, nvec, lane);
             }
             // ragged tail (only a per-tensor view can have one: rows == 1): straight from global memory
             if (tail > 0 && lane == 0) {
