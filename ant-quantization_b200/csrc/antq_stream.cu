@@ -76,6 +76,7 @@ struct StreamParams {
     long long rows, cols;
     unsigned total_chunks, chunks_per_cta, chunks_rem;   // CTA b owns chunks_per_cta (+1 if b < chunks_rem) chunks
     int alpha_per_row, chunks_per_row, chunk_elems;
+    int cpr_shift;      // log2(chunks_per_row) when it is a power of two, else -1
     int nt_real, mid, ovp_index, n_entries;
     float gmax, lim;
     int debug;          // ANTQ_DEBUG experiments: 2 = no chain (copy through), 16 = no FMA twin, 128 = one-phase OVP
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
     auto geo_of = [&](int k) {
         Geo g;
         const unsigned c = c_begin + (unsigned)k;
-        g.row = c / cpr;
+        g.row = p.cpr_shift >= 0 ? c >> p.cpr_shift : c / cpr;        // chunks per row is usually a power of two
         const long long col0 = (long long)(c - g.row * cpr) * p.chunk_elems;
         const long long remain = p.cols - col0;
         const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
@@ -834,7 +835,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
             }
             const unsigned row = g.row;
             const unsigned rl = p.alpha_per_row ? row - row_begin : 0u;        // CTA-local row = table index
-            if (lane == 0) antqs_st_release(cons_row + warp, rl);              // builders may recycle slots of rows < rl
+            // builders may recycle the slots of rows < rl: a plain store is enough -- every table value this warp read
+            // for an earlier row has long been consumed, so there is nothing for a release fence to order
+            if (lane == 0) *reinterpret_cast<volatile unsigned *>(cons_row + warp) = rl;
             {
                 const unsigned g = rl / G;
                 const unsigned *flag = built + (g % GS);
@@ -1016,6 +1019,12 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     const long long cpr = (cols + p.chunk_elems - 1) / p.chunk_elems;
     if (cpr > 0x7fffffffLL) return ANTQ_ENOTSUP;
     p.chunks_per_row = (int)cpr;
+    p.cpr_shift = -1;
+    if ((cpr & (cpr - 1)) == 0) {
+        int sh = 0;
+        while ((1LL << sh) < cpr) sh++;
+        p.cpr_shift = sh;
+    }
     const long long total = rows * cpr;
     if (total == 0) return 0;
     if (total > 0x7fffffffLL) return ANTQ_ENOTSUP;
