@@ -503,3 +503,38 @@ def test_short_rows_olive(antq, kind, signed):
     ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
     y = _run_olive(antq, x, alpha, grid, outl, True, False, 0)
     assert_bit_equal(y, ref, "olive short rows")
+
+
+@pytest.mark.parametrize("kind,olive", [("flint", False), ("int", False), ("flint", True)])
+def test_full_size_properties(antq, kind, olive):
+    """BASELINE.json's largest sweep size (16384 x 16384 fp16 = 512 MB, 111 rows per CTA: row-table ring reuse) through
+    size-independent properties: the stream kernel agrees with the independent generic flat kernel everywhere, with the
+    oracle on a sample of rows, every output is a codebook level times the row's scale, and the op is idempotent."""
+    from antq import _lib
+    N = 16384
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(N, N, device=dev(), generator=g) * 0.03).to(torch.float16)
+    x[::997, ::13] *= 40                                                  # clipped / outlier values
+    if olive:
+        grid, outl = orc.olive_grid(kind, 4, True), orc.olive_outlier_grid(4, True)
+        cb = _cb(antq, grid, outl)
+        alpha = (3 * x.float().std(1)).contiguous()
+    else:
+        grid, outl = orc.ant_grid(kind, 4, True), None
+        cb = _cb(antq, grid)
+        alpha = (x.float().abs().amax(1) * 0.85).contiguous()
+    assert antq.fakequant_plan(x, cb, True, ovp=olive) == 1
+    y = antq.fakequant(x, alpha, cb, True, ovp=olive)
+    yf = antq.fakequant(x, alpha, cb, True, ovp=olive, flags=_lib.FLAG_FORCE_FLAT)
+    assert torch.equal(y.view(torch.int16), yf.view(torch.int16)), "stream kernel != flat kernel"
+    del yf
+    rows = torch.arange(0, N, 331, device=dev())                             # 50 rows against the oracle
+    xs, als = x[rows].cpu().numpy(), alpha[rows].cpu().numpy()
+    ref = orc.olive_forward(xs, als, grid, outl, per_row=True) if olive else orc.ant_forward(xs, als, grid, per_row=True)
+    assert_bit_equal(to_np(y[rows]), ref, "oracle on sampled rows")
+    if not olive:
+        # idempotence: quantized values are fixed points of the same quantizer
+        y2 = antq.fakequant(y, alpha, cb, True)
+        assert torch.equal(y2.view(torch.int16), y.view(torch.int16)), "not idempotent"
+        # at most 2^bit distinct values per row
+        assert int(torch.unique(y[12345]).numel()) <= 16
