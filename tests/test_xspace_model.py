@@ -78,3 +78,46 @@ def test_olive_concat_thresholds():
     assert np.array_equal(cb["levels"][rank], z)
     zc, codes = orc.scan(d, grid, want_codes=True)
     assert np.array_equal(cb["codes"][rank], codes)
+
+
+FOLDED = [("int", 3, True), ("int", 4, True), ("int", 5, True), ("flint", 4, True), ("pot", 4, True), ("float2", 4, True)]
+
+
+@pytest.mark.parametrize("kind,bit,signed", FOLDED)
+def test_folded_xspace_exhaustive(kind, bit, signed):
+    """Symmetric codebooks and signed int-k ('symmetric + one extra negative level', ANTQ_CB_SYMX) as the stream kernel
+    runs them: magnitude thresholds X / Xn on |x| plus one signed compare for the extra level -- every fp16 pattern."""
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = xm.prepare_codebook(grid)
+    fs = xm.fold_signs(cb)
+    assert fs is not None and fs["symx"] == (kind == "int") and fs["nt"] == 2 ** (bit - 1) - 1
+    gmax = grid.max()
+    for s in scales(gmax)[:14]:
+        alpha = f32(s * gmax)
+        s_eff = f32(alpha / gmax)
+
+        def exact(xs):
+            return orc.ant_forward(xs, alpha, grid, per_row=False)
+        got, _ = xm.forward_fast_folded(ALL_F16, s_eff, cb, np.float16, exact)
+        ref = orc.ant_forward(ALL_F16, alpha, grid, per_row=False)
+        same = (got.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got) & np.isnan(ref))
+        assert same.all(), (kind, bit, s, ALL_F16[~same][:5], got[~same][:5], ref[~same][:5])
+
+
+@pytest.mark.parametrize("kind,bit,signed", FOLDED + [("flint", 4, False), ("int", 4, False)])
+def test_dspace_chain_exhaustive(kind, bit, signed):
+    """The short-row kernel's algorithm (true division, compare chain against the exact d-space thresholds, literal STE)
+    on every fp16 pattern; asymmetric codebooks compare d itself."""
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = xm.prepare_codebook(grid)
+    gmax = grid.max()
+    for s in scales(gmax)[:14]:
+        alpha = f32(s * gmax)
+        s_eff = f32(alpha / gmax)
+
+        def exact(xs):
+            return orc.ant_forward(xs, alpha, grid, per_row=False)
+        got, _ = xm.forward_dspace(ALL_F16, s_eff, cb, np.float16, exact)
+        ref = orc.ant_forward(ALL_F16, alpha, grid, per_row=False)
+        same = (got.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got) & np.isnan(ref))
+        assert same.all(), (kind, bit, s, ALL_F16[~same][:5], got[~same][:5], ref[~same][:5])

@@ -143,3 +143,78 @@ def forward_fast(x, s, cb, dtype, exact_fn):
     if slow.any():
         out[slow] = exact_fn(x[slow])
     return out, slow
+
+
+# ---- symmetric / "symmetric + one extra negative level" (SYMX) forms used by the CUDA kernels ---------------------
+def fold_signs(cb):
+    """What antq_prepare_kernel derives for a codebook that is symmetric about a zero level (L odd) or symmetric except
+    for ONE extra level at the negative end (L even, signed int-k):  mid = index of the zero level, magnitude thresholds
+    tpos[i] (d >= 0: magnitude i+1 wins iff d >= tpos[i]) and tneg[i] (d < 0: ... iff -d >= tneg[i]), n_mag magnitudes
+    present on both sides, and for SYMX the d-space threshold thr[0] below which the extra level level[0] wins."""
+    L, T = cb["levels"], cb["thr"]
+    n = len(L)
+    mid = n >> 1
+    sym = n % 2 == 1 and n >= 3 and L[mid] == 0 and all(L[mid + k] == -L[mid - k] for k in range(1, mid + 1))
+    symx = (not sym) and n % 2 == 0 and n >= 4 and L[mid] == 0 and all(L[mid + k] == -L[mid - k] for k in range(1, mid))
+    if not (sym or symx):
+        return None
+    nt = mid if sym else mid - 1
+    tpos = np.array([T[mid + i] for i in range(nt)], dtype=f32)
+    tneg = np.array([_unord(_ord(f32(-T[mid - i - 1])) + 1) for i in range(nt)], dtype=f32)
+    return dict(sym=sym, symx=symx, mid=mid, nt=nt, tpos=tpos, tneg=tneg,
+                thr_e=T[0] if symx else None, lev_e=L[0] if symx else None)
+
+
+def forward_dspace(x, s, cb, dtype, exact_fn):
+    """antq_short_kernel: d = fl32(x / s), compare chain against the codebook's d-space thresholds, literal STE."""
+    x = np.asarray(x, dtype=dtype)
+    fs = fold_signs(cb)
+    with np.errstate(all="ignore"):
+        d = (x.astype(f32) / f32(s)).astype(f32)
+        ad = np.abs(d)
+        neg = np.signbit(d)
+        if fs is None:
+            rank = (d[:, None] >= cb["thr"][None, :]).sum(1)
+            q = cb["levels"][rank]
+        else:
+            t = np.where(neg[:, None], fs["tneg"][None, :], fs["tpos"][None, :])
+            rank = (ad[:, None] >= t).sum(1)
+            q = np.copysign(cb["levels"][fs["mid"] + rank], d).astype(f32)
+            if fs["symx"]:
+                q = np.where(d < fs["thr_e"], fs["lev_e"], q).astype(f32)
+        out = (((q - d).astype(f32) + d).astype(f32) * f32(s)).astype(f32).astype(dtype)
+        lim_idx = f32(65536.0)
+        slow = ~(ad <= lim_idx)
+    if slow.any():
+        out[slow] = exact_fn(x[slow])
+    return out, slow
+
+
+def forward_fast_folded(x, s, cb, dtype, exact_fn):
+    """antq_stream_kernel for SYMMETRIC / SYMX codebooks: x-space thresholds on |x| (X for x >= 0, Xn for x < 0),
+    outputs O = RN(level * s) with the sign of x, and for SYMX one signed compare x < Xe for the extra level."""
+    x = np.asarray(x, dtype=dtype)
+    fs = fold_signs(cb)
+    assert fs is not None
+    if not (np.isfinite(s) and s > 0):
+        return exact_fn(x), np.ones(x.shape, bool)
+    X = np.array([x_threshold_exact(t, s, dtype) for t in fs["tpos"]], dtype=dtype)
+    Xn = np.array([x_threshold_exact(t, s, dtype) for t in fs["tneg"]], dtype=dtype)
+    with np.errstate(all="ignore"):
+        O = (cb["levels"][fs["mid"]:fs["mid"] + fs["nt"] + 1] * f32(s)).astype(f32).astype(dtype)
+        ax = np.abs(x)
+        neg = x < 0                                   # -0 counts as positive, like HSET2.LT
+        t = np.where(neg[:, None], Xn[None, :], X[None, :])
+        rank = (ax[:, None] >= t).sum(1)
+        out = O[rank]
+        out = np.where(np.signbit(x) & (rank > 0), -out, out).astype(dtype)
+        if fs["symx"]:
+            Xe = x_threshold_exact(fs["thr_e"], s, dtype)
+            Oe = (f32(fs["lev_e"]) * f32(s)).astype(f32).astype(dtype)
+            out = np.where(x < Xe, Oe, out).astype(dtype)
+        lim = f32(2.0) * min(cb["vmax"], -cb["vmin"])
+        xlim = f32(lim) * f32(s) * f32(1 - 2.0 ** -10)
+        slow = ~(np.abs(x.astype(f32)) <= xlim)
+    if slow.any():
+        out[slow] = exact_fn(x[slow])
+    return out, slow
