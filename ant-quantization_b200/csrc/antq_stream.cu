@@ -296,7 +296,8 @@ __device__ __forceinline__ void build_tables(RowTab &t, const StreamParams &p, f
         }
 
         // FMA-pipe twin
-        bool ok = row_ok && NT <= 15 && (!ties || NT <= 7 || (OVP && NT == 15)) && !(p.debug & 16);   // (two-phase OVP runs
+        bool ok = row_ok && (NT <= 15 || (OVP && !SYM && NT == 31)) && (!ties || NT <= 7 || (OVP && NT == 15)) &&
+                  !(p.debug & 16);   // (two-phase OVP runs
         // its 7-threshold normal chain with the tie-aware FMA twin; the full 15-threshold chain never does)
         // S = 2^k with xlim * S in [2^13, 2^14): every in-window |x| stays finite after scaling
         int k = 13 - (int)((__float_as_uint(xl) >> 23) & 0xff) + 127;
@@ -576,20 +577,21 @@ __device__ __forceinline__ bool run_chunk(CH &ch, const uint32_t *tab, const uin
     return ch.special(xlim);
 }
 
-// OliVe, signed 4-bit (7 normal + 7 outlier thresholds on |x|), 16-bit types.  Outliers are rare (|x| beyond ~3 sigma),
-// but a 14-threshold chain + pair masking for every element costs twice the normal chain.  Two phases instead:
-//   1. every vector runs the 7-threshold NORMAL chain (exactly the ANT flint/int path; no pair can be masked if no
+// OliVe 4-bit, 16-bit types: signed = 7 normal + 7 outlier thresholds on |x| (NT1 = 7, NT2 = 15), unsigned = 15 + 15
+// thresholds on x (NT1 = 15, NT2 = 31).  Outliers are rare (|x| beyond ~3 sigma), but the full chain + pair masking for
+// every element costs twice the normal chain.  Two phases instead:
+//   1. every vector runs the NORMAL chain (exactly the ANT flint/int path; no pair can be masked if no
 //      element of the vector is an outlier) and remembers whether its max |x| reaches the first outlier threshold;
 //   2. the few vectors that hold an outlier are compacted into a per-warp list in shared memory and redone -- densely,
 //      one vector per lane -- with the full 14-threshold chain and the outlier-victim mask, from the staged copy.
-template <typename T, int MODE1, bool TIES2>
+template <typename T, int NT1, int NT2, bool SYM, int MODE1, bool TIES2>
 __device__ __forceinline__ bool run_chunk_ovp2(const uint32_t *tab, const uint4 *sv, uint4 *og, int nvec, int lane,
                                                uint32_t s2, uint32_t xo, uint32_t xon, uint32_t xlim,
                                                unsigned char *list, int debug) {
     typedef typename Pack2<T>::v2 v2;
-    Chain16<T, 7, true, false, false, MODE1, 16> c1;
+    Chain16<T, NT1, SYM, false, false, MODE1, NT2 + 1> c1;
     c1.load(tab, s2, xo, xon);
-    c1.E[7] = 0u;                                                   // slot 7 of the 16-pitch table is E[7], not O[0] = 0
+    c1.E[NT1] = tab[2 * (NT2 + 1) + NT2];                           // O[0] lives in slot NT2 of the full-pitch table
     const v2 xo2 = Pack2<T>::from_u32(xo);                          // positive-side threshold: <= the negative-side one
     uint32_t pend = 0;                                              // bit j: vector j * 32 + lane holds an outlier
     const uint4 *sp = sv + lane;
@@ -636,7 +638,7 @@ __device__ __forceinline__ bool run_chunk_ovp2(const uint32_t *tab, const uint4 
             list[pos++] = (unsigned char)(j * 32 + lane);
         }
         __syncwarp();          // the list is complete; phase-1 stores to these vectors are ordered before the rewrites
-        Chain16<T, 15, true, true, false, TIES2 ? kModeTies : kModeAlu> c2;
+        Chain16<T, NT2, SYM, true, false, TIES2 ? kModeTies : kModeAlu> c2;
         c2.load(tab, s2, xo, xon);
 #pragma unroll 1
         for (int i = lane; i < total; i += 32) {
@@ -866,13 +868,24 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
                         // signed 4-bit OliVe: normal chain for everything, full chain only for the vectors with an outlier
                         unsigned char *list = ovp_list + warp * 256;
                         if ((flags & kRowTies) && (flags & kRowFma))
-                            special = run_chunk_ovp2<T, kModeTiesMix, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, 7, 15, true, kModeTiesMix, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else if (flags & kRowTies)
-                            special = run_chunk_ovp2<T, kModeTies, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, 7, 15, true, kModeTies, true>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else if (flags & kRowFma)
-                            special = run_chunk_ovp2<T, kModeMix, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, 7, 15, true, kModeMix, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         else
-                            special = run_chunk_ovp2<T, kModeAlu, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                            special = run_chunk_ovp2<T, 7, 15, true, kModeAlu, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        done = true;
+                    }
+                }
+                if constexpr (sizeof(T) == 2 && OVP && !SYM && NT == 31) {
+                    if (p.ovp_index == 15 && !(p.debug & 128)) {
+                        // unsigned 4-bit OliVe (post-ReLU inputs): 15 normal thresholds first, all 30 only where needed
+                        unsigned char *list = ovp_list + warp * 256;
+                        if (flags & kRowFma)
+                            special = run_chunk_ovp2<T, 15, 31, false, kModeMix, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
+                        else
+                            special = run_chunk_ovp2<T, 15, 31, false, kModeAlu, false>(tab, sv, ov, nvec, lane, m0.w, m1.x, m1.y, xlim, list, p.debug);
                         done = true;
                     }
                 }
