@@ -23,3 +23,5 @@ from antq.quantizer import QuantBase, Quantizer, TensorQuantizer
 Conv2dQuantizer, LinearQuantizer, _Conv1dQuantizer, MultiheadAttentionQuantizer = make_layers(TensorQuantizer)
 for _c in (Conv2dQuantizer, LinearQuantizer, MultiheadAttentionQuantizer):
     _c.__module__ = __name__
+# names BASELINE.json / papers use for the same wrappers (the reference classes are *Quantizer)
+QuantConv2d, QuantLinear = Conv2dQuantizer, LinearQuantizer

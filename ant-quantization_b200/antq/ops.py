@@ -142,6 +142,22 @@ def fakequant(x, alpha, cb, per_row, ovp=False, want_codes=False, flags=0, out=N
     return (out, codes) if want_codes else out
 
 
+def fakequant_grouped(x, alpha, cb, group_size, ovp=False, out=None):
+    """Group-wise scales (one alpha per `group_size` consecutive elements of the flat tensor: group-8/16/32/128 ...):
+    the tensor is viewed as [numel / group_size, group_size] and quantized per row.  Groups shorter than 512 elements
+    take antq_short_kernel, longer ones the stream kernel.  alpha: fp32, numel / group_size entries."""
+    _need_cuda(x, "x")
+    if not x.is_contiguous():
+        raise RuntimeError("antq: x must be contiguous")
+    g = int(group_size)
+    if g <= 0 or x.numel() % g:
+        raise ValueError("antq: numel (%d) is not a multiple of the group size (%d)" % (x.numel(), g))
+    xv = x.view(-1, g)
+    ov = None if out is None else out.view(-1, g)
+    y = fakequant(xv, alpha, cb, True, ovp=ovp, out=ov)
+    return y.view(x.shape) if out is None else out
+
+
 def fakequant_plan(x, cb, per_row, ovp=False, flags=0):
     rows, cols = _rows_cols(x, per_row)
     fl = flags | (_lib.FLAG_OVP if ovp else 0)

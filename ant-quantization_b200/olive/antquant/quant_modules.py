@@ -21,3 +21,5 @@ from antq.quantizer import OliveTensorQuantizer as TensorQuantizer
 Conv2dQuantizer, LinearQuantizer, Conv1dQuantizer, _MHA = make_layers(TensorQuantizer)
 for _c in (Conv2dQuantizer, LinearQuantizer, Conv1dQuantizer):
     _c.__module__ = __name__
+# names BASELINE.json / papers use for the same wrappers (the reference classes are *Quantizer)
+QuantConv2d, QuantLinear = Conv2dQuantizer, LinearQuantizer

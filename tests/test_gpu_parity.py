@@ -538,3 +538,22 @@ def test_full_size_properties(antq, kind, olive):
         assert torch.equal(y2.view(torch.int16), y.view(torch.int16)), "not idempotent"
         # at most 2^bit distinct values per row
         assert int(torch.unique(y[12345]).numel()) <= 16
+
+
+@pytest.mark.parametrize("group", [8, 32, 128, 1024])
+def test_group_scales(antq, group):
+    """Group-wise scales through antq.fakequant_grouped (BASELINE.json's group-8/16/32 sweep): one alpha per `group`
+    consecutive elements = the per-row path on the [numel / group, group] view."""
+    rng = np.random.default_rng(group)
+    grid = orc.ant_grid("flint", 4, True)
+    x = (rng.standard_normal((512, 4096)) * 0.05).astype(np.float16)
+    xg = x.reshape(-1, group)
+    alpha = (np.abs(xg.astype(np.float32)).max(1) * 0.9).astype(np.float32)
+    cb = _cb(antq, grid)
+    xd = torch.from_numpy(x).to(dev())
+    y = antq.fakequant_grouped(xd, torch.from_numpy(alpha).to(dev()), cb, group)
+    assert y.shape == xd.shape
+    ref = orc.ant_forward(xg, alpha, grid, per_row=True).reshape(x.shape)
+    assert_bit_equal(to_np(y), ref, "group %d" % group)
+    with pytest.raises(ValueError):
+        antq.fakequant_grouped(xd[:, :4095].contiguous(), torch.from_numpy(alpha).to(dev()), cb, group)
