@@ -39,7 +39,7 @@ print("after sync     ", stat(synced))
 print("CTA end        ", stat(end), "  span %.2f us" % (end.max()))
 for slot, name in ((3, "b0 build enter"), (5, "b0 scale known"), (6, "b0 thresholds "), (4, "b0 build done ")):
     print(name, stat(rel(t[:, slot])))
-for k in (0, 1, 2, 3, 4, 8, 12, 16, 20, 23, 24, 25, 26, 27):
+for k in (0, 1, 2, 4, 8, 11, 12, 16, 23, 24, 32, 40, 48, 52, 53, 54, 55):
     v = valid[:, k]
     if v.sum() == 0: continue
     c = ch[v, k, :]
