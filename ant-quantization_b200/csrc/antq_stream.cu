@@ -775,11 +775,10 @@ __global__ void __launch_bounds__(kThreads, 1) antq_stream_kernel(const StreamPa
 #endif
         }
     };
-    // Consumer w owns chunks w, w + kNC, ... and a private ring of kRing stages (w, w + kNC, ...): the chunk after the
-    // one being computed is always in flight, so an SM has kNC * (kRing - 1) * 8 KiB outstanding -- the HBM
-    // latency-bandwidth product -- and no more (requesting the whole ring at start-up makes every SM's FIRST chunk queue
-    // behind ~30 MB of other requests: profiles/r01_notes.md).  No issuer warp, no `empty` barriers: the warp that
-    // frees a stage is the one that refills it.
+    // Consumer warp w owns two private stages (w and w + kNC): the chunk after the one being computed is always in
+    // flight, so an SM has kNC x 4 KiB outstanding -- the HBM latency-bandwidth product -- and no more (requesting a whole
+    // deep ring at start-up makes every SM's FIRST chunk queue behind ~30 MB of other requests: profiles/r01_notes.md).
+    // No issuer warp, no `empty` barriers: the warp that frees a stage is the one that refills it.
     // Chunks are handed out by a shared counter at the moment a warp REQUESTS them (one ahead of the one it computes):
     // rows with ties or out-of-window values cost more than others, and a CTA's chunk count rarely divides by kNC.
     auto claim = [&]() {
