@@ -141,3 +141,36 @@ RESULT["has_dist"] = hasattr(qm, "dist")
     assert res["out"] == [-384, -256, -192, -128, -96, -64, -48, 48, 64, 96, 128, 192, 256, 384]
     assert res["conv1d"] == "Conv1dQuantizer"
     assert res["has_dist"] is False
+
+
+@pytest.mark.parametrize("flavor,mode", [("ant", "ant-int-pot-flint"), ("olive", "ant-int-flint")])
+def test_weight_cache_key_host_logic(flavor, mode):
+    """The weight-quant cache key (antq/layers.py) without a GPU: absent before calibration and under QAT autograd,
+    present in eval, and different after every change the quantized weight depends on."""
+    res, _ = run(flavor, r'''
+import antq.layers as L
+lin = nn.Linear(64, 32)
+q = LinearQuantizer(mode=%r, wbit=4, abit=4, args=mkargs(%r))
+q.set_param(lin)
+q.quant_weight.enable_quantization("w")
+RESULT["before_init"] = q._weight_key() is None
+q.quant_weight.has_inited_quant_para.data = torch.ones_like(q.quant_weight.has_inited_quant_para)
+with torch.no_grad():
+    k0 = q._weight_key()
+    q.weight.mul_(2.0)
+    k1 = q._weight_key()
+    q.quant_weight.alpha.data = q.quant_weight.alpha.data * 0.5
+    k2 = q._weight_key()
+    q.quant_weight.quant_grid.data = q.quant_weight.quant_grid.data.clone()
+    k3 = q._weight_key()
+    q.quant_weight.is_enable_weight = False
+    k4 = q._weight_key()
+    q.quant_weight.is_enable_weight = True
+RESULT["keys_differ"] = k0 is not None and len({k0, k1, k2, k3, k4}) == 5
+RESULT["stable"] = q._weight_key() == q._weight_key()
+RESULT["under_grad"] = q._weight_key() is None if %r == "ant" else q._weight_key() is not None
+L.CACHE_WEIGHTS = False
+with torch.no_grad():
+    RESULT["switched_off"] = q._weight_key() is None
+''' % (mode, mode, flavor))
+    assert res["before_init"] and res["keys_differ"] and res["stable"] and res["under_grad"] and res["switched_off"], res
