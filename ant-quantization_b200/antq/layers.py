@@ -41,13 +41,32 @@ def make_layers(TensorQuantizer):
             self.bias = _copy_param(getattr(src, "bias", None))
 
         # Weight-quant cache: the reference re-fake-quantizes the weight on every forward
-        # (A/antquant/quant_modules.py:611-617); when nothing the result depends on has changed -- the weight, alpha,
-        # the grid (+ outliers), the enable flags -- and autograd is not recording, the previous result is returned:
-        # identical output, one launch and one pass over the weight less per forward.  `antq.layers.CACHE_WEIGHTS =
-        # False` (or ANTQ_CACHE_WEIGHTS=0) restores the reference's behaviour exactly.
+        # (A/antquant/quant_modules.py:611-617).  In EVAL mode, when nothing the result depends on has changed -- the
+        # weight, alpha, the grid (+ outliers), the enable flags -- and autograd is not recording, the previous result
+        # is returned: identical output, one launch and one pass over the weight less per forward.
+        # Invalidation: the key holds (data_ptr, _version) of every tensor involved; train(), load_state_dict(),
+        # .to()/.cuda()/.half() and invalidate_weight_cache() drop the cache outright; training mode never caches
+        # (optimizers update `p.data` in place, which bumps no version counter).  An in-place `.data` edit of an
+        # eval-mode module is the one thing the key cannot see: call invalidate_weight_cache() after it, or set
+        # `antq.layers.CACHE_WEIGHTS = False` (ANTQ_CACHE_WEIGHTS=0) for the reference's behaviour exactly.
+        def invalidate_weight_cache(self):
+            self._wq_key = self._wq_val = None
+
+        def train(self, mode=True):
+            self.invalidate_weight_cache()
+            return super().train(mode)
+
+        def _apply(self, fn, *a, **kw):
+            self.invalidate_weight_cache()
+            return super()._apply(fn, *a, **kw)
+
+        def _load_from_state_dict(self, *a, **kw):
+            self.invalidate_weight_cache()
+            return super()._load_from_state_dict(*a, **kw)
+
         def _weight_key(self):
             q, w = self.quant_weight, self.weight
-            if not CACHE_WEIGHTS or not q._is_inited():
+            if not CACHE_WEIGHTS or self.training or not q._is_inited():
                 return None
             if torch.is_grad_enabled() and (w.requires_grad or q.alpha.requires_grad) and q.flavor != "olive":
                 return None                                  # QAT: the fake-quant must stay on the autograd tape
@@ -140,9 +159,12 @@ def make_layers(TensorQuantizer):
 
         def set_param(self, MA):
             self.embed_dim, self.num_heads, self.dropout = MA.embed_dim, MA.num_heads, MA.dropout
-            self.kdim, self.vdim, self.batch_first = MA.kdim, MA.vdim, MA.batch_first
+            self.kdim = MA.kdim if MA.kdim is not None else MA.embed_dim
+            self.vdim = MA.vdim if MA.vdim is not None else MA.embed_dim
+            self.batch_first = MA.batch_first
             self._qkv_same_embed_dim = self.kdim == self.embed_dim and self.vdim == self.embed_dim
             if not self._qkv_same_embed_dim:
+                # the reference cannot build this case either (undefined `factory_kwargs`, A/...multihead_attention.py:570)
                 raise NotImplementedError("MultiheadAttentionQuantizer: packed in_proj (kdim == vdim == embed_dim) only")
             self.head_dim = self.embed_dim // self.num_heads
             assert self.head_dim * self.num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
@@ -155,48 +177,82 @@ def make_layers(TensorQuantizer):
             self.out_proj_bias = _copy_param(MA.out_proj.bias)
             self.bias_k = _copy_param(MA.bias_k)
             self.bias_v = _copy_param(MA.bias_v)
-            if self.bias_k is not None or self.add_zero_attn:
-                raise NotImplementedError("MultiheadAttentionQuantizer: bias_k/bias_v/add_zero_attn are not supported")
 
         def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=True, attn_mask=None,
                     average_attn_weights=True):
+            """A/antquant/multihead_attention.py:663-687 + the attention math of :214-480 (packed in-projection,
+            bias_k / bias_v rows, the zero-attention column, bool / float masks merged with the key-padding mask)."""
             w_in = self.in_quant_weight(self.in_proj_weight)
-            x = self.in_quant_input(query)
+            x = self.in_quant_input(query)                               # key and value ARE the quantized query (:665-666)
             w_out = self.out_quant_weight(self.out_proj_weight)
             batched = x.dim() == 3
             if not batched:
                 x = x.unsqueeze(1)
+                if key_padding_mask is not None:
+                    key_padding_mask = key_padding_mask.unsqueeze(0)
             elif self.batch_first:
                 x = x.transpose(0, 1)
             L, N, E = x.shape                                            # (seq, batch, embed)
+            H, hd = self.num_heads, self.head_dim
             q, k, v = F.linear(x, w_in, self.in_proj_bias).chunk(3, dim=-1)
-            heads = lambda t: t.contiguous().view(L, N * self.num_heads, self.head_dim).transpose(0, 1)
-            q, k, v = heads(q), heads(k), heads(v)
-            mask = None
-            if attn_mask is not None:
-                mask = attn_mask
-                if mask.dtype == torch.bool:
-                    mask = torch.zeros_like(mask, dtype=q.dtype).masked_fill_(mask, float("-inf"))
-                if mask.dim() == 2:
-                    mask = mask.unsqueeze(0)
-            if key_padding_mask is not None:
-                kpm = key_padding_mask.view(N, 1, 1, L).expand(-1, self.num_heads, -1, -1).reshape(N * self.num_heads, 1, L)
-                if kpm.dtype == torch.bool:
-                    kpm = torch.zeros_like(kpm, dtype=q.dtype).masked_fill_(kpm, float("-inf"))
-                mask = kpm if mask is None else mask + kpm
-            scores = torch.bmm(q / math.sqrt(self.head_dim), k.transpose(-2, -1))
+            mask = attn_mask
             if mask is not None:
-                scores = scores + mask
+                if mask.dtype == torch.uint8:
+                    mask = mask.to(torch.bool)
+                if mask.dim() == 2:
+                    if tuple(mask.shape) != (L, L):
+                        raise RuntimeError("The shape of the 2D attn_mask is %s, but should be %s." % (tuple(mask.shape), (L, L)))
+                    mask = mask.unsqueeze(0)
+                elif mask.dim() == 3:
+                    if tuple(mask.shape) != (N * H, L, L):
+                        raise RuntimeError("The shape of the 3D attn_mask is %s, but should be %s." % (tuple(mask.shape), (N * H, L, L)))
+                else:
+                    raise RuntimeError("attn_mask's dimension %d is not supported" % mask.dim())
+            kpm = key_padding_mask
+            if kpm is not None and kpm.dtype == torch.uint8:
+                kpm = kpm.to(torch.bool)
+            if self.bias_k is not None and self.bias_v is not None:
+                k = torch.cat([k, self.bias_k.repeat(1, N, 1)])
+                v = torch.cat([v, self.bias_v.repeat(1, N, 1)])
+                if mask is not None:
+                    mask = F.pad(mask, (0, 1))
+                if kpm is not None:
+                    kpm = F.pad(kpm, (0, 1))
+            q = q.contiguous().view(L, N * H, hd).transpose(0, 1)
+            k = k.contiguous().view(k.shape[0], N * H, hd).transpose(0, 1)
+            v = v.contiguous().view(v.shape[0], N * H, hd).transpose(0, 1)
+            if self.add_zero_attn:
+                zeros = (N * H, 1, hd)
+                k = torch.cat([k, torch.zeros(zeros, dtype=k.dtype, device=k.device)], dim=1)
+                v = torch.cat([v, torch.zeros(zeros, dtype=v.dtype, device=v.device)], dim=1)
+                if mask is not None:
+                    mask = F.pad(mask, (0, 1))
+                if kpm is not None:
+                    kpm = F.pad(kpm, (0, 1))
+            S = k.size(1)
+            if kpm is not None:
+                assert tuple(kpm.shape) == (N, S), "expecting key_padding_mask shape of %s, but got %s" % ((N, S), tuple(kpm.shape))
+                kpm = kpm.view(N, 1, 1, S).expand(-1, H, -1, -1).reshape(N * H, 1, S)
+                if mask is None:
+                    mask = kpm
+                elif mask.dtype == torch.bool:
+                    mask = mask.logical_or(kpm)
+                else:
+                    mask = mask.masked_fill(kpm, float("-inf"))
+            if mask is not None and mask.dtype == torch.bool:
+                mask = torch.zeros_like(mask, dtype=q.dtype).masked_fill_(mask, float("-inf"))
+            q = q / math.sqrt(hd)
+            scores = torch.baddbmm(mask, q, k.transpose(-2, -1)) if mask is not None else torch.bmm(q, k.transpose(-2, -1))
             attn = F.softmax(scores, dim=-1)
             if self.training and self.dropout > 0.0:
                 attn = F.dropout(attn, p=self.dropout)
             ctx = torch.bmm(attn, v).transpose(0, 1).contiguous().view(L, N, E)
-            out = F.linear(self.out_quant_input(ctx), w_out, self.out_proj_bias)
+            out = F.linear(self.out_quant_input(ctx), w_out, self.out_proj_bias)      # (:459-460)
             weights = None
             if need_weights:
-                weights = attn.view(N, self.num_heads, L, L)
+                weights = attn.view(N, H, L, S)
                 if average_attn_weights:
-                    weights = weights.sum(dim=1) / self.num_heads
+                    weights = weights.sum(dim=1) / H
             if not batched:
                 out = out.squeeze(1)
                 weights = None if weights is None else weights.squeeze(0)

@@ -44,6 +44,8 @@ class Codebook:
     def __init__(self, buf, info, k_normal, k_out):
         self.buf = buf
         self.info = info
+        self.ptr = buf.data_ptr()
+        self.info_ref = ctypes.byref(info)
         self.k_normal = k_normal
         self.k_out = k_out
 
@@ -99,11 +101,21 @@ def _rows_cols(x, per_row):
 
 def _alpha_arg(alpha, rows, per_row, device):
     a = alpha
-    if not (a.dtype is torch.float32 and a.device == device and a.is_contiguous() and not a.requires_grad):
+    # only the pointer is read: a Parameter (requires_grad) is as good as its .detach()
+    if not (a.dtype is torch.float32 and a.device == device and a.is_contiguous()):
         a = alpha.detach().to(device=device, dtype=torch.float32).contiguous()
     if a.numel() != (rows if per_row else 1):
         raise ValueError("antq: alpha has %d entries, expected %d" % (a.numel(), rows if per_row else 1))
     return a
+
+
+def _check_out(out, x, name="out"):
+    """A caller-supplied output buffer is handed to the kernel as a raw pointer: refuse anything that is not a
+    same-sized, same-typed, contiguous tensor on x's device instead of writing out of bounds."""
+    if not (isinstance(out, torch.Tensor) and out.dtype is x.dtype and out.device == x.device and
+            out.numel() == x.numel() and out.is_contiguous()):
+        raise ValueError("antq: `%s` must be a contiguous %s tensor with %d elements on %s" %
+                         (name, x.dtype, x.numel(), x.device))
 
 
 class _maybe_guard:
@@ -121,24 +133,43 @@ class _maybe_guard:
             self.g.__exit__(*exc)
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream       # (device index) -> cudaStream_t as int, no Stream object
+_antq_fakequant = lib.antq_fakequant
+
+
 def fakequant(x, alpha, cb, per_row, ovp=False, want_codes=False, flags=0, out=None):
     """Fused scale -> nearest -> (OVP) -> STE -> rescale.  x: contiguous CUDA tensor;
     alpha: fp32 CUDA tensor with x.shape[0] entries (per_row) or one entry.
     No allocation when `out` is given, no synchronisation: safe under CUDA-graph capture."""
-    _need_cuda(x, "x")
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        _need_cuda(x, "x")
     if not x.is_contiguous():
         raise RuntimeError("antq: x must be contiguous")
-    with _maybe_guard(x.device):
-        rows, cols = _rows_cols(x, per_row)
-        a = _alpha_arg(alpha, rows, per_row, x.device)
+    dev = x.device
+    guard = None if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    if guard is not None:
+        guard.__enter__()
+    try:
+        if per_row:
+            rows = x.shape[0] if x.dim() > 0 else 1
+            cols = x.numel() // rows if rows else 0
+        else:
+            rows, cols = 1, x.numel()
+        a = _alpha_arg(alpha, rows, per_row, dev)
         if out is None:
             out = torch.empty_like(x)
-        codes = torch.empty(x.shape, dtype=torch.int16, device=x.device) if want_codes else None
+        else:
+            _check_out(out, x)
+        codes = torch.empty(x.shape, dtype=torch.int16, device=dev) if want_codes else None
         fl = flags | (_lib.FLAG_OVP if ovp else 0)
-        check(lib.antq_fakequant(x.data_ptr(), out.data_ptr(), codes.data_ptr() if want_codes else None,
-                                 a.data_ptr(), int(bool(per_row)), rows, cols, _dtype_code(x), cb.buf.data_ptr(),
-                                 ctypes.byref(cb.info), fl, torch.cuda.current_stream().cuda_stream),
-              "antq_fakequant")
+        rc = _antq_fakequant(x.data_ptr(), out.data_ptr(), codes.data_ptr() if want_codes else None,
+                             a.data_ptr(), 1 if per_row else 0, rows, cols, _DT[x.dtype], cb.ptr,
+                             cb.info_ref, fl, _raw_stream(dev.index))
+        if rc:
+            check(rc, "antq_fakequant")
+    finally:
+        if guard is not None:
+            guard.__exit__(None, None, None)
     return (out, codes) if want_codes else out
 
 
@@ -153,6 +184,8 @@ def fakequant_grouped(x, alpha, cb, group_size, ovp=False, out=None):
     if g <= 0 or x.numel() % g:
         raise ValueError("antq: numel (%d) is not a multiple of the group size (%d)" % (x.numel(), g))
     xv = x.view(-1, g)
+    if out is not None:
+        _check_out(out, x)
     ov = None if out is None else out.view(-1, g)
     y = fakequant(xv, alpha, cb, True, ovp=ovp, out=ov)
     return y.view(x.shape) if out is None else out
@@ -194,6 +227,7 @@ class HostPipeline:
 
     def __init__(self, device=0, chunk_bytes=8 << 20, n_stages=3):
         self._h = ctypes.c_void_p()
+        self._keep = []
         check(lib.antq_host_create(ctypes.byref(self._h), int(device), int(chunk_bytes), int(n_stages)),
               "antq_host_create")
 
@@ -215,6 +249,9 @@ class HostPipeline:
         for t in (x, out, alpha, grid):
             if t.is_cuda:
                 raise RuntimeError("HostPipeline takes host tensors")
+        if not x.is_contiguous():
+            raise RuntimeError("antq: x must be contiguous")
+        _check_out(out, x)
         rows, cols = _rows_cols(x, per_row)
         a = alpha.detach().to(torch.float32).reshape(-1).contiguous()
         g = grid.detach().to(torch.float32).reshape(-1).contiguous()
@@ -223,10 +260,13 @@ class HostPipeline:
         check(fn(self._h, _ptr(x), _ptr(out), _ptr(a), int(bool(per_row)), rows, cols,
                  _dtype_code(x), _ptr(g), g.numel(), _ptr(o), 0 if o is None else o.numel(),
                  _lib.FLAG_OVP if ovp else 0), "antq_host_fakequant")
+        if not sync:
+            self._keep.append((x, out, a))           # the copies read / write these after the call returns
         return out
 
     def synchronize(self):
         check(lib.antq_host_synchronize(self._h), "antq_host_synchronize")
+        del self._keep[:]
 
     @property
     def last_launches(self):

@@ -122,6 +122,8 @@ class Quantizer(nn.Module):
 
         self._cb = None
         self._cb_key = None
+        self._cb_src = None
+        self._ovp = self.flavor == "olive" and not bool(getattr(self.args, "no_outlier", False))
         self._inited_key = None
         self._inited_val = False
 
@@ -189,13 +191,22 @@ class Quantizer(nn.Module):
 
     def _codebook(self, device):
         """Prepared device codebook, rebuilt only when the grid buffers change
-        (load_state_dict / load_ant_state_dict / type search assign new tensors)."""
+        (load_state_dict / load_ant_state_dict / type search assign new tensors).  When only the VERSION of a
+        buffer moved (DDP's broadcast_buffers copies rank 0's buffers in place before every forward) the contents
+        are compared on the device first, so an unchanged grid costs one tiny compare instead of a rebuild."""
         g = self.quant_grid
         o = None if self._no_outlier() else self.outliers
-        key = (g.data_ptr(), g._version, g.numel(), str(device),
+        key = (g.data_ptr(), g._version, g.numel(), device,
                None if o is None else (o.data_ptr(), o._version, o.numel()))
         if key != self._cb_key:
-            self._cb = ops.prepare_codebook(g.to(device), None if o is None else o.to(device))
+            old = self._cb_key
+            same = False
+            if old is not None and self._cb_src is not None and old[0] == key[0] and old[2:4] == key[2:4] and \
+                    (o is None) == (old[4] is None) and (o is None or (old[4][0], old[4][2]) == (key[4][0], key[4][2])):
+                same = bool(torch.equal(g, self._cb_src[0]) and (o is None or torch.equal(o, self._cb_src[1])))
+            if not same:
+                self._cb = ops.prepare_codebook(g.to(device), None if o is None else o.to(device))
+                self._cb_src = (g.detach().clone(), None if o is None else o.detach().clone())
             self._cb_key = key
         return self._cb
 
@@ -203,14 +214,14 @@ class Quantizer(nn.Module):
     def _launch(self, x, alpha):
         if not x.is_cuda:
             raise RuntimeError("antquant (B200): quantization needs CUDA tensors; there is no CPU fallback")
-        xc = x if x.is_contiguous() else x.contiguous()
-        cb = self._codebook(xc.device)
-        return ops.fakequant(xc, alpha, cb, self.is_perchannel, ovp=not self._no_outlier()).view(x.shape)
+        if x.is_contiguous():
+            return ops.fakequant(x, alpha, self._codebook(x.device), self.is_perchannel, self._ovp)
+        xc = x.contiguous()
+        return ops.fakequant(xc, alpha, self._codebook(xc.device), self.is_perchannel, self._ovp).view(x.shape)
 
     def _forward(self, data, display=False):
         if self.flavor == "olive" or not torch.is_grad_enabled() or not (data.requires_grad or self.alpha.requires_grad):
-            with torch.no_grad():
-                return self._launch(data, self.alpha.detach())
+            return self._launch(data, self.alpha)         # the kernel only reads alpha's storage: no graph is recorded
         return _FakeQuantSTE.apply(data, self.alpha, self)
 
     # -------------------------------------------------------------- calibration
@@ -297,16 +308,19 @@ class Quantizer(nn.Module):
         self.mode = names[int(np.argsort(np.array(scores))[0])]
 
     def outlier_set(self, data):
-        """OLAccel-style baseline (mode == 'outlier', A/...:417-436)."""
+        """OLAccel-style baseline (mode == 'outlier', A/...:417-436): the int-4 window ends at the `percent`
+        percentile of |x| (np.percentile on the host, like the reference), the 16-bit window at max |x|."""
         def reduce_ave(t):
             rt = t.clone()
             if _dist_on():
                 dist.all_reduce(rt, op=dist.ReduceOp.SUM)
                 rt /= dist.get_world_size()
             return rt
-        self.percent_value_int4 = torch.tensor(np.percentile(data.abs().float().cpu().numpy(), self.percent * 100),
-                                               device=data.device, dtype=torch.float32)
-        self.percent_value_int16 = data.abs().max().float()
+        host = data.abs().cpu()
+        if host.dtype in (torch.float16, torch.bfloat16):
+            host = host.float()
+        self.percent_value_int4 = torch.tensor(np.percentile(host.numpy(), self.percent * 100), device=data.device)
+        self.percent_value_int16 = data.abs().max()
         self.percent_value_int4.data = reduce_ave(self.percent_value_int4.data)
         self.percent_value_int16.data = reduce_ave(self.percent_value_int16.data)
         if _rank0():
@@ -316,19 +330,27 @@ class Quantizer(nn.Module):
         self.has_inited_quant_para.data = torch.ones_like(self.has_inited_quant_para)
 
     def outlier_quant(self, data):
-        """A/...:438-465."""
-        mask_int16 = data.abs() > self.percent_value_int4
-        if self.percent_value_int4 > 0:
-            tensor = self._launch(data.detach(), self.percent_value_int4.reshape(())).clone()
+        """A/...:438-465, op for op: the int-4 part is `nearest(data / scale) * scale` -- no STE sum, unlike
+        `_forward` -- so it goes through antq_lut_nearest (the scan kernel's drop-in), not the fused kernel."""
+        p4, p16 = self.percent_value_int4, self.percent_value_int16
+        mask_int16 = data.abs() > p4
+        if p4 > 0:
+            scale = p4 / torch.max(self.quant_grid)
+            data_int4 = (data / scale).detach()
+            quant_data = ops.lut_nearest(data_int4.contiguous(), self._codebook(data.device)).view(data.shape)
+            tensor = quant_data * scale
         else:
             tensor = data.clone().detach()
         level = 2 ** 16 - 1 if self.is_signed else 2 ** 15 - 1
         if self.percent < 100:
-            scale = (self.percent_value_int16 - self.percent_value_int4) / level
-            big = data[mask_int16]
-            q = ((big.abs() - self.percent_value_int4) / scale).round() * scale + self.percent_value_int4
-            q = q * big.sign()
-            tensor[mask_int16] = (q - tensor[mask_int16]).detach() + tensor[mask_int16]
+            scale = (p16 - p4) / level
+            data_int16 = data[mask_int16].abs()
+            sign_int16 = data[mask_int16].sign()
+            data_int16 = data_int16 - p4
+            quant_data = (data_int16 / scale).round() * scale
+            quant_data = quant_data + p4
+            quant_data = quant_data * sign_int16
+            tensor[mask_int16] = (quant_data - tensor[mask_int16]).detach() + tensor[mask_int16]
         return tensor
 
     def _is_inited(self):
@@ -398,8 +420,9 @@ class Quantizer(nn.Module):
                 return tensor
         elif not self.is_enable_weight:
             return tensor
-        with torch.no_grad():
-            self._init_quant_para(tensor, input_tensor)
+        if not self._is_inited():
+            with torch.no_grad():
+                self._init_quant_para(tensor, input_tensor)
         if self.flavor == "ant" and self.mode == 'outlier':
             return self.outlier_quant(tensor)
         return self._forward(tensor)

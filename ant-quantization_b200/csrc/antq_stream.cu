@@ -935,11 +935,15 @@ template <typename T, int NT, bool SYM, bool OVP, bool XNEG = false>
 int launch_kernel(const StreamParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_stream_kernel<T, NT, SYM, OVP, XNEG>;
     const int smem = kNS * kChunkMax + kRT * TabGeom<NT>::kTabBytes + kNS * 8 + (kRT + kNC + 4) * 4 + kNC * 256 + 16;
-    static bool configured = false;      // per instantiation; the attribute is idempotent
-    if (!configured) {
+    // The opt-in is per device (context): one bit per device ordinal, per instantiation.
+    static unsigned long long configured = 0ull;
+    int dev = 0;
+    cudaError_t ed = cudaGetDevice(&dev);
+    if (ed != cudaSuccess) return (int)ed;
+    if (dev >= 64 || !((configured >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        if (dev < 64) configured |= 1ull << dev;
     }
     static int pdl = -1;
     if (pdl < 0) { const char *v = getenv("ANTQ_PDL"); pdl = (v && atoi(v) == 0) ? 0 : 1; }

@@ -202,7 +202,7 @@ args = mkargs("ant-int-flint", w_up=150, a_up=150, w_low=75, a_low=75)
 lin = nn.Linear(512, 256).to(dev)
 q = LinearQuantizer(mode="ant-int-flint", wbit=4, abit=4, args=args)
 q.set_param(lin)
-q = q.to(dev)
+q = q.to(dev).eval()                          # the cache is an eval-mode feature
 q.quant_weight.enable_quantization("w"); q.quant_input.enable_quantization("a")
 x = torch.randn(64, 512, device=dev)
 with torch.no_grad():
@@ -229,6 +229,14 @@ if %(ant)s:
     q.train()
     yt = q(x)
     grad_key = q._wq_key is None and yt.requires_grad
+    q.eval()
+with torch.no_grad():
+    q(x); q(x)
+    warm = q._wq_key is not None
+    q.invalidate_weight_cache(); inval = q._wq_key is None
+    q(x); q.load_state_dict(q.state_dict()); sd_inval = q._wq_key is None
+    q(x); q.train(); tr_inval = q._wq_key is None; q(x); tr_off = q._wq_key is None
+RESULT.update(hooks=bool(warm and inval and sd_inval and tr_inval and tr_off))
 RESULT.update(hit=bool(hit), same=bool(torch.equal(y1, y2) and torch.equal(y2, y_nocache)),
               w_inval=bool(torch.equal(y3, y3_ref) and not torch.equal(y3, y2)),
               a_inval=bool(torch.equal(y4, y4_ref) and not torch.equal(y4, y3)), grad=grad_key)
@@ -236,3 +244,4 @@ RESULT.update(hit=bool(hit), same=bool(torch.equal(y1, y2) and torch.equal(y2, y
     res, _ = run(tree, body, timeout=600)
     assert res["hit"] and res["same"] and res["w_inval"] and res["a_inval"], res
     assert res["grad"] in (True, "n/a"), res
+    assert res["hooks"], res

@@ -1,0 +1,220 @@
+"""Model-shaped parity (BASELINE.json C2-C4): random-init ResNet-50, a BERT-base
+shaped encoder, OPT, GPT-2 (Conv1D), a torchvision ViT (nn.MultiheadAttention), standalone MultiheadAttention variants
+and the `outlier` mode go through THIS repo's antquant mirror on the GPU and are compared with fixtures produced by the
+UNMODIFIED reference Python on the same seeded models (tests/golden/make_golden_models.py).
+
+Three bars per model:
+  pinned   with the reference's calibrated (mode, sign, alpha, grid, outliers) loaded, every weight quantizer's output
+           and every activation quantizer fed the reference's own input must be BIT-IDENTICAL (CRC-32 of the bytes);
+           logits then agree to float-accumulation noise amplified by the few activations a 1-ulp conv difference flips
+           (rel L2 bound written below).
+  calib    calibrating from scratch with the fused sweep must pick the same (type, sign) and the same alpha
+           (fractions asserted below; near-ties between alpha candidates are decided by fp32 summation order).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from host_util import ROOT, run
+
+pytestmark = pytest.mark.gpu
+
+ZOO_BODY = r'''
+import zlib
+sys.path.insert(0, %(tests)r)
+import model_zoo
+name = %(name)r
+dev = torch.device("cuda:0")
+fix = dict(np.load(os.path.join(%(golden)r, "zoo_%%s.npz" %% name)))
+meta = json.load(open(os.path.join(%(golden)r, "zoo_%%s.json" %% name)))
+tree, build = model_zoo.ZOO[name]
+model, xs, kw, args = build()
+ck = model_zoo.fp32_checksum(model)
+RESULT["checksum_rel"] = abs(ck - meta["fp32_checksum"]) / meta["fp32_checksum"]
+for i, x in enumerate(xs):
+    assert np.array_equal(x.numpy(), fix["x%%d" %% i]), "seeded input differs from the fixture"
+crc = lambda t: zlib.crc32(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes())
+logits = model_zoo.logits_of
+xs_d = tuple(x.to(dev) for x in xs)
+
+def fresh():
+    set_quantizer(args)
+    q = quantize_model(model)
+    enable_quantization(q)
+    return q.to(dev).eval()
+
+# ---------------- pinned: the reference's calibration result loaded into our modules ----------------
+q = fresh()
+quants = {n: m for n, m in q.named_modules() if isinstance(m, TensorQuantizer)}
+ref = {e["name"]: e for e in meta["quantizers"]}
+RESULT["same_names"] = sorted(quants) == sorted(ref)
+for n, e in ref.items():
+    if not e["called"]:
+        continue
+    m = quants[n]
+    m.mode, m.is_signed = e["mode"], e["signed"]
+    m.alpha.data = torch.from_numpy(fix["q/%%s/alpha" %% n]).to(dev)
+    m.quant_grid.data = torch.from_numpy(fix["q/%%s/grid" %% n]).to(dev)
+    if ("q/%%s/outliers" %% n) in fix:
+        m.outliers.data = torch.from_numpy(fix["q/%%s/outliers" %% n]).to(dev)
+    m.has_inited_quant_para.data = torch.ones_like(m.has_inited_quant_para)
+rec = {}
+hs = [m.register_forward_hook(lambda mod, inp, o, n=n: rec.__setitem__(n, o)) for n, m in quants.items()]
+with torch.no_grad():
+    y = logits(q(*xs_d, **kw))
+for h in hs:
+    h.remove()
+w_bad, w_n, a_bad, a_n = [], 0, [], 0
+for n, e in ref.items():
+    if not e["called"]:
+        continue
+    if not e["is_input"]:
+        w_n += 1
+        if crc(rec[n]) != e["crc"]:
+            w_bad.append(n)
+    elif e.get("has_input"):
+        a_n += 1
+        with torch.no_grad():
+            o = quants[n](torch.from_numpy(fix["q/%%s/in" %% n]).to(dev))
+        if crc(o) != e["crc"]:
+            a_bad.append(n)
+yr = torch.from_numpy(fix["y"]).to(dev)
+RESULT.update(w_n=w_n, w_bad=w_bad, a_n=a_n, a_bad=a_bad,
+              pinned_rel=float((y - yr).norm() / yr.norm()),
+              quant_effect=float((torch.from_numpy(fix["y_fp32"]).to(dev) - yr).norm() / yr.norm()))
+
+# ---------------- calib: our own calibration from scratch ----------------
+q2 = fresh()
+with torch.no_grad():
+    y_cal = logits(q2(*xs_d, **kw))
+    y2 = logits(q2(*xs_d, **kw))
+quants2 = {n: m for n, m in q2.named_modules() if isinstance(m, TensorQuantizer)}
+mode_ok = sign_ok = n_q = 0
+rel = []
+weight_mode_ok = weight_n = 0
+for n, e in ref.items():
+    if not e["called"]:
+        continue
+    m = quants2[n]
+    n_q += 1
+    mode_ok += m.mode == e["mode"]
+    sign_ok += bool(m.is_signed) == e["signed"]
+    if not e["is_input"]:
+        weight_n += 1
+        weight_mode_ok += m.mode == e["mode"]
+    a_ref = torch.from_numpy(fix["q/%%s/alpha" %% n]).to(dev).reshape(-1).float()
+    a = m.alpha.detach().reshape(-1).float()
+    if m.mode == e["mode"] and a.numel() == a_ref.numel():
+        rel.append(((a - a_ref).abs() / a_ref.abs().clamp_min(1e-30)).cpu())
+rel = torch.cat(rel)
+RESULT.update(n_q=n_q, mode_ok=int(mode_ok), sign_ok=int(sign_ok), weight_n=weight_n, weight_mode_ok=int(weight_mode_ok),
+              alpha_exact_frac=float((rel <= 1e-6).float().mean()), alpha_p99=float(rel.quantile(0.99)) if rel.numel() < 1e7 else -1.0,
+              alpha_max=float(rel.max()),
+              calib_rel=float((y2 - yr).norm() / yr.norm()),
+              cal_rel=float((y_cal - torch.from_numpy(fix["y_cal"]).to(dev)).norm() / yr.norm()))
+'''
+
+
+@pytest.mark.parametrize("name", ["vit", "gpt2", "opt2", "bert2", "resnet50"])
+def test_zoo_model_matches_reference(name):
+    if not os.path.exists(os.path.join(GOLDEN, "zoo_%s.npz" % name)):
+        pytest.skip("fixture zoo_%s.npz not generated" % name)
+    import model_zoo
+    tree = model_zoo.ZOO[name][0]
+    res, out = run(tree, ZOO_BODY % dict(tests=os.path.join(ROOT, "tests"), golden=GOLDEN, name=name), timeout=1500)
+    print(json.dumps(res))
+    assert res["checksum_rel"] < 1e-12, "random init differs from the fixture's: %r" % res["checksum_rel"]
+    assert res["same_names"]
+    # pinned: every quantizer output bit-identical to the reference's
+    assert res["w_n"] > 0 and res["w_bad"] == [], res
+    assert res["a_n"] > 0 and res["a_bad"] == [], res
+    # logits: GPU GEMM / conv accumulation order differs from the CPU's, and a 1-ulp change in a pre-quantizer
+    # activation can move it across a 4-bit threshold; the bound is 2 % of the logits' norm and at most a fifth of
+    # the quantization effect itself (|y_fp32 - y_quant|)
+    assert res["pinned_rel"] < 2e-2 and res["pinned_rel"] < 0.2 * max(res["quant_effect"], 1e-3), res
+    # calibration from scratch: same sign everywhere, same type on >= 90 % of the quantizers (a type flips only when
+    # two candidates' summed MSEs agree to fp32 noise), alpha identical on >= 90 % of the channels
+    assert res["sign_ok"] == res["n_q"], res
+    assert res["mode_ok"] >= 0.9 * res["n_q"], res
+    assert res["alpha_exact_frac"] >= 0.9, res
+    assert res["calib_rel"] < 0.25 * max(res["quant_effect"], 1e-2) + 2e-2, res
+
+
+MODULES_BODY = r'''
+dev = torch.device("cuda:0")
+fix = dict(np.load(os.path.join(%(golden)r, "modules_ant.npz")))
+meta = json.load(open(os.path.join(%(golden)r, "modules_ant.json")))
+def bits_equal(a, b):
+    a = a.detach().cpu().numpy(); b = np.asarray(b)
+    return a.shape == b.shape and bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+mha = {}
+for c in meta["mha"]:
+    t = "mha/%%s/" %% c["tag"]
+    E, H = 64, 4
+    ma = nn.MultiheadAttention(E, H, bias=c["bias"], add_bias_kv=c["add_bias_kv"], add_zero_attn=c["add_zero_attn"],
+                               batch_first=c["batch_first"]).eval()
+    if not c["bias"]:
+        ma.out_proj.bias = nn.Parameter(torch.zeros(E))
+    ma.load_state_dict({k[len(t) + 5:]: torch.from_numpy(v) for k, v in fix.items() if k.startswith(t + "fp32/")})
+    set_quantizer(mkargs("ant-int-pot-flint"))
+    q = quantize_model(ma)
+    enable_quantization(q)
+    sd = {k[len(t) + 3:]: torch.from_numpy(v) for k, v in fix.items() if k.startswith(t + "sd/")}
+    for n, m in q.named_modules():
+        if isinstance(m, TensorQuantizer):                 # buffers are re-sized to the checkpoint's, as load_ant_state_dict does
+            m.quant_grid.data = sd[n + ".quant_grid"].clone(); m.alpha.data = sd[n + ".alpha"].clone()
+            m.mode = c["modes"][n]
+    missing = q.load_state_dict({k: (v.to(q.state_dict()[k].dtype) if k in q.state_dict() else v) for k, v in sd.items()}, strict=True)
+    q = q.to(dev).eval()
+    r = {"keys": sorted(sd) == sorted(q.state_dict())}
+    # each of the four quantizers, pinned, on the reference's own input: bit-exact
+    for n, m in q.named_modules():
+        if isinstance(m, TensorQuantizer):
+            with torch.no_grad():
+                o = m(torch.from_numpy(fix[t + "qin/" + n]).to(dev))
+            r["q_" + n] = bits_equal(o, fix[t + "qout/" + n])
+    x = torch.from_numpy(fix[t + "x"]).to(dev)
+    am = torch.from_numpy(fix[t + "attn_mask"]).to(dev) if (t + "attn_mask") in fix else None
+    kpm = torch.from_numpy(fix[t + "kpm"]).to(dev) if (t + "kpm") in fix else None
+    with torch.no_grad():
+        y, w = q(x, x, x, key_padding_mask=kpm, attn_mask=am, average_attn_weights=False)
+    yr, wr = torch.from_numpy(fix[t + "y"]).to(dev), torch.from_numpy(fix[t + "w"]).to(dev)
+    r["y_shape"] = list(y.shape) == list(yr.shape); r["w_shape"] = list(w.shape) == list(wr.shape)
+    r["y_rel"] = float((y - yr).norm() / yr.norm()); r["w_err"] = float((w - wr).abs().max())
+    mha[c["tag"]] = r
+RESULT["mha"] = mha
+
+outl = {}
+for c in meta["outlier"]:
+    t = c["tag"]
+    x = torch.from_numpy(fix[t + "x"]).to(dev)
+    tq = TensorQuantizer(mode="outlier", bit=4, is_signed=c["signed"], is_enable=True, is_input=True,
+                         args=mkargs("outlier", percent=c["percent"]))
+    tq.enable_quantization("o")
+    tq = tq.to(dev)
+    with torch.no_grad():
+        y_cal = tq(x)
+        y = tq(x * 1.01)
+    outl[t] = dict(y_cal=bits_equal(y_cal, fix[t + "y_cal"]), y=bits_equal(y, fix[t + "y"]),
+                   p4=float(tq.percent_value_int4) == float(fix[t + "p4"]), p16=float(tq.percent_value_int16) == float(fix[t + "p16"]),
+                   grid=bits_equal(tq.quant_grid, fix[t + "grid"]), signed=bool(tq.is_signed) == c["is_signed_after"],
+                   dtypes=[str(tq.percent_value_int4.dtype), str(tq.percent_value_int16.dtype)] == [c["p4_dtype"], c["p16_dtype"]])
+RESULT["outlier"] = outl
+'''
+
+
+def test_mha_variants_and_outlier_mode_match_reference():
+    """a-9 (MultiheadAttentionQuantizer incl. bias_k / add_zero_attn / masks / unbatched) and a-10 (`outlier` mode,
+    A/antquant/quant_modules.py:417-465) against fixtures from the unmodified reference."""
+    res, _ = run("ant", MODULES_BODY % dict(golden=GOLDEN), timeout=900)
+    for tag, r in res["mha"].items():
+        assert r["keys"] and r["y_shape"] and r["w_shape"], (tag, r)
+        for k, v in r.items():
+            if k.startswith("q_"):
+                assert v, "MHA %s: quantizer %s is not bit-exact on the reference's input" % (tag, k[2:])
+        assert r["y_rel"] < 2e-2 and r["w_err"] < 2e-2, (tag, r)
+    for tag, r in res["outlier"].items():
+        assert all(r.values()), (tag, r)

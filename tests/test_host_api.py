@@ -152,6 +152,7 @@ import antq.layers as L
 lin = nn.Linear(64, 32)
 q = LinearQuantizer(mode=%r, wbit=4, abit=4, args=mkargs(%r))
 q.set_param(lin)
+q.eval()
 q.quant_weight.enable_quantization("w")
 RESULT["before_init"] = q._weight_key() is None
 q.quant_weight.has_inited_quant_para.data = torch.ones_like(q.quant_weight.has_inited_quant_para)
@@ -169,8 +170,10 @@ with torch.no_grad():
 RESULT["keys_differ"] = k0 is not None and len({k0, k1, k2, k3, k4}) == 5
 RESULT["stable"] = q._weight_key() == q._weight_key()
 RESULT["under_grad"] = q._weight_key() is None if %r == "ant" else q._weight_key() is not None
+with torch.no_grad():
+    q.train(); RESULT["train_off"] = q._weight_key() is None; q.eval()
 L.CACHE_WEIGHTS = False
 with torch.no_grad():
     RESULT["switched_off"] = q._weight_key() is None
 ''' % (mode, mode, flavor))
-    assert res["before_init"] and res["keys_differ"] and res["stable"] and res["under_grad"] and res["switched_off"], res
+    assert res["before_init"] and res["keys_differ"] and res["stable"] and res["under_grad"] and res["switched_off"] and res["train_off"], res
