@@ -1,0 +1,104 @@
+"""numpy model of the PIECEWISE-UNIFORM (PU) closed-form codec used by antq_pu.cu -- every fp32 operation of the
+kernel's fast path is one numpy float32 operation here (numpy never contracts to FMA; the kernel is built with
+--fmad=false and uses explicit _rn intrinsics), so checking this model against the oracle on every fp16 bit pattern
+checks the kernel's arithmetic.
+
+Idea.  Every grid the reference generates for int / flint / pot / float (A/antquant/quant_modules.py:157-278) is
+`fl32(k * c)` for integers k (c = the smallest positive level), and inside each octave [2^e, 2^(e+1)) the k's form a
+uniform progression with a power-of-two step 2^(e - mb_e).  So the nearest level of d is found WITHOUT a scan:
+    t  = x * kx                    kx ~ 1 / (s c), a few ulps off
+    mf = (t + M_e) - M_e           M_e = 1.5 * 2^23 * step_e : round t to a multiple of step_e (the octave's magic)
+    q  = fl32(clamp(mf, kmin, kmax) * c);   out = fl32(q * s)        (STE is exact inside the window)
+and the result is provably the reference's unless t lies within delta_e of a midpoint (then the element is redone
+with the literal arithmetic: true division + exact thresholds).  delta_e = 2^(e - 19) covers the error of t
+(<= 5 ulp), of the levels (1 ulp) and of the scan's rounded distances (1-2 ulp) with margin.
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def _bits(a):
+    return np.asarray(a, dtype=f32).view(np.uint32)
+
+
+def analyze(grid):
+    """Returns the PU description of a codebook, or None when the grid is not piecewise uniform."""
+    lev = np.unique(np.asarray(grid, dtype=f32))
+    lev = lev[~np.isnan(lev)]
+    lev = np.where(lev == 0, f32(0), lev).astype(f32)
+    lev = np.unique(lev)
+    if not (lev == 0).any() or not (lev > 0).any():
+        return None
+    c = lev[lev > 0].min()
+    k = np.rint(lev / c).astype(f32)
+    if np.abs(k).max() >= 2 ** 20 or not np.array_equal((k * c).astype(f32), lev):
+        return None
+    kmin, kmax = k.min(), k.max()
+    U = np.unique(np.abs(k[k != 0])).astype(np.int64)
+    pos = k[k > 0].astype(np.int64)
+    neg = (-k[k < 0]).astype(np.int64)
+    if not np.array_equal(np.sort(pos), U[U <= kmax]) or not np.array_equal(np.sort(neg), U[U <= -kmin]):
+        return None
+    e_top = int(np.floor(np.log2(U.max())))
+    ls = []                                                    # log2(step) per octave 0 .. e_top
+    for e in range(e_top + 1):
+        Ue = U[(U >= 2 ** e) & (U < 2 ** (e + 1))]
+        if Ue.size == 0 or Ue[0] != 2 ** e:
+            return None
+        if Ue.size == 1:
+            # a lone level: the octave's step is the octave itself -- except at the top, where anything beyond is
+            # clamped anyway and keeping the previous octave's step keeps int-k uniform (signed int-k: {1 .. 2^B})
+            step = 2 ** e if (e < e_top or e == 0) else 2 ** ls[e - 1]
+        else:
+            step = int(Ue[1] - Ue[0])
+        if step & (step - 1) or step > 2 ** e:
+            return None
+        full = np.arange(2 ** e, 2 ** (e + 1), step)
+        if e < e_top:
+            if not np.array_equal(Ue, full):
+                return None
+        elif not np.array_equal(Ue, full[:Ue.size]):           # the top octave may be truncated (clamped afterwards)
+            return None
+        ls.append(int(np.log2(step)))
+    magic = np.zeros(256, dtype=f32)
+    delta = np.zeros(256, dtype=f32)
+    for E in range(256):
+        e = min(max(E - 127, 0), e_top)
+        magic[E] = f32(1.5 * 2.0 ** (23 + ls[e]))
+        delta[E] = f32(2.0 ** (e - 19))
+    uniform = all(v == 0 for v in ls)
+    return dict(c=f32(c), inv_c=f32(f32(1) / c), kmin=f32(kmin), kmax=f32(kmax), magic=magic, delta=delta,
+                e_top=e_top, ls=ls, uniform=uniform)
+
+
+def forward(x, s, pu, lim, exact, out_dtype):
+    """x: array of out_dtype; s: fp32 scale (alpha / max(grid)); lim: the codebook's exact window in d-space.
+    `exact(xs)` is the literal reference arithmetic for the flagged elements.  Returns (out, flagged)."""
+    s = f32(s)
+    xf = x.astype(f32)
+    with np.errstate(all="ignore"):
+        rs = f32(1) / s
+        kx = f32(rs * pu["inv_c"])
+        t = (xf * kx).astype(f32)
+        E = (_bits(t) >> 23) & 0xff
+        M = pu["magic"][E]
+        dl = pu["delta"][E]
+        mf = ((t + M).astype(f32) - M).astype(f32)
+        r = (t - mf).astype(f32)
+        h = (_bits(M) - np.uint32((24 << 23) | 0x400000)).view(f32)
+        v = (np.abs(r) - h).astype(f32)
+        near = np.abs(v) <= dl
+        mfc = np.minimum(np.maximum(mf, pu["kmin"]), pu["kmax"]).astype(f32)
+        q = (mfc * pu["c"]).astype(f32)
+        o = (q * s).astype(f32)
+        xl = f32(f32(f32(lim) * s) * f32(0.9990234375))
+        window = np.abs(xf) <= xl                                 # False for NaN
+        row_ok = bool(s > 0) and bool(np.isfinite(s)) and bool(np.isfinite(kx)) and bool(kx > 0)
+    flagged = near | ~window
+    if not row_ok:
+        flagged = np.ones_like(flagged)
+    out = o.astype(out_dtype)
+    if flagged.any():
+        out[flagged] = exact(x[flagged])
+    return out, flagged
