@@ -7,20 +7,33 @@
 
 #include "antq_common.cuh"
 
-int antq_launch_rows(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
-                     long long cols, int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp,
-                     cudaStream_t st);
 int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                        int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
 int antq_launch_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                       int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
 int antq_short_thresholds(const antq_codebook_info *info, bool ovp);
+int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
+int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                         int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
 int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
 int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
 int antq_launch_mse_sweep(const void *x, const float *base_alpha, int alpha_per_row, const float *ratios, int n_cand,
                           double *err, long long rows, long long cols, int dtype, const AntqCodebook *cb, bool ovp,
                           cudaStream_t st);
+
+int antq_num_sms() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 
 namespace {
 inline int esize(int dtype) { return dtype == ANTQ_F32 ? 4 : (dtype == ANTQ_F16 || dtype == ANTQ_BF16) ? 2 : 0; }
@@ -32,8 +45,8 @@ extern "C" {
 int antq_abi_version(void) { return ANTQ_ABI_VERSION; }
 
 const char *antq_build_info(void) {
-    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_short_kernel antq_rows_kernel antq_flat_kernel antq_absmax_kernel "
-           "antq_mse_sweep_kernel; built " __DATE__;
+    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_pu_stream_kernel antq_pu_short_kernel antq_short_kernel "
+           "antq_flat_kernel antq_absmax_kernel antq_mse_sweep_kernel; built " __DATE__;
 }
 
 const char *antq_error_string(int status) {
@@ -70,24 +83,36 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     if (es == 0 || rows < 0 || cols < 0) return ANTQ_EINVAL;
     if (flags & ANTQ_FLAG_FORCE_FLAT) return 2;
     const bool ovp = (flags & ANTQ_FLAG_OVP) != 0;
-    bool ok = info != nullptr;
-    if (ok) {
+    const int vec = 16 / es;
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const bool exact = info && (info->flags & ANTQ_CB_WELLSEP) && (info->flags & ANTQ_CB_STE_EXACT) && aligned && !codes;
+    // closed form (antq_pu.cu): any piecewise-uniform grid, no OVP
+    const bool pu = exact && (info->flags & ANTQ_CB_PU) && !ovp && !(flags & ANTQ_FLAG_NO_PU);
+    const bool long_rows = (cols >= kRowsMinCols || (flags & ANTQ_FLAG_FORCE_ROWS)) && (cols % vec == 0 || rows == 1);
+    bool chain = false;
+    int nt = 0;
+    if (exact) {
         const bool sym = (info->flags & ANTQ_CB_SYMMETRIC) != 0;
-        // signed int-k grids run as "symmetric + one extra negative level" in the stream kernel (no code output)
-        const bool symx = !sym && (info->flags & ANTQ_CB_SYMX) && !ovp && !codes;
-        const int nt = (sym || symx) ? info->n_mag - 1 : info->n_levels - 1;
-        const int vec = 16 / es;
-        ok = (info->flags & ANTQ_CB_WELLSEP) && (info->flags & ANTQ_CB_STE_EXACT) && nt >= 1 && nt <= 31;
-        ok = ok && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)codes % 16 == 0);
-        ok = ok && (cols % vec == 0 || rows == 1);
-        ok = ok && (!ovp || ((info->flags & ANTQ_CB_OVP_OK) && cols % 2 == 0));
-        ok = ok && (cols >= kRowsMinCols || (flags & ANTQ_FLAG_FORCE_ROWS));
+        // signed int-k grids run as "symmetric + one extra negative level" in the stream kernel
+        const bool symx = !sym && (info->flags & ANTQ_CB_SYMX) && !ovp;
+        nt = (sym || symx) ? info->n_mag - 1 : info->n_levels - 1;
+        chain = nt >= 1 && nt <= 31 && long_rows && (!ovp || ((info->flags & ANTQ_CB_OVP_OK) && cols % 2 == 0));
     }
-    if (ok) return 1;
-    if (flags & ANTQ_FLAG_FORCE_ROWS) return ANTQ_ENOTSUP;
-    // short rows / scale groups: the d-space chain kernel (no code output, <= 15 thresholds after folding signs)
-    if (info && !codes && (info->flags & ANTQ_CB_WELLSEP) && rows > 1 && cols < kRowsMinCols && cols % (16 / es) == 0 &&
-        ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && antq_short_thresholds(info, ovp) >= 1 &&
+    if (flags & ANTQ_FLAG_FORCE_ROWS) return chain ? 1 : ANTQ_ENOTSUP;
+    if (flags & ANTQ_FLAG_FORCE_PU) {
+        if (pu && long_rows) return 4;
+        if (pu && rows > 1 && cols % vec == 0) return 5;
+        return ANTQ_ENOTSUP;
+    }
+    // the compare chain wins while it is short (<= 7 thresholds after folding signs: every signed 4-bit grid, OliVe's
+    // two-phase chain); beyond that the closed form does (unsigned 4-bit, 5 to 8 bit)
+    if (chain && (nt <= 7 || !pu)) return 1;
+    if (pu && long_rows) return 4;
+    if (chain) return 1;
+    const bool short_rows = info && !codes && aligned && rows > 1 && cols < kRowsMinCols && cols % vec == 0;
+    if (short_rows && pu) return 5;
+    // short rows / scale groups of the other grids: the d-space chain kernel (<= 15 thresholds after folding signs)
+    if (short_rows && (info->flags & ANTQ_CB_WELLSEP) && antq_short_thresholds(info, ovp) >= 1 &&
         antq_short_thresholds(info, ovp) <= 15 && (!ovp || (info->flags & ANTQ_CB_OVP_OK)))
         return 3;
     return 2;
@@ -106,25 +131,19 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
     const int plan = antq_fakequant_plan(info, rows, cols, dtype, flags, x, out, codes);
     if (plan < 0) return plan;
     const AntqCodebook *cb = (const AntqCodebook *)codebook;
-    if (plan == 1) {
-        // hot path: the persistent producer/consumer kernel; the per-warp row kernel keeps the code-emitting variant
-        static int use_rows = -1;
-        if (use_rows < 0) { const char *e = getenv("ANTQ_KERNEL"); use_rows = (e && !strcmp(e, "rows")) ? 1 : 0; }
-        if (!codes && !use_rows) {
-            const int rc = antq_launch_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
-                                              (cudaStream_t)stream);
-            if (rc != ANTQ_ENOTSUP) return rc;
-        }
-        return antq_launch_rows(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
-                                (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ANTQ_ENOTSUP;
+    switch (plan) {
+        case 1: rc = antq_launch_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp, st); break;
+        case 3: rc = antq_launch_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp, st); break;
+        case 4: rc = antq_launch_pu_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, st); break;
+        case 5: rc = antq_launch_pu_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, st); break;
+        default: break;
     }
-    if (plan == 3) {
-        const int rc = antq_launch_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp,
-                                         (cudaStream_t)stream);
-        if (rc != ANTQ_ENOTSUP) return rc;
-    }
-    return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp,
-                            (cudaStream_t)stream);
+    if (rc != ANTQ_ENOTSUP) return rc;
+    if (flags & (ANTQ_FLAG_FORCE_ROWS | ANTQ_FLAG_FORCE_PU)) return ANTQ_ENOTSUP;
+    // every shape, alignment and grid: the generic kernel (also the only one that emits int16 code indices)
+    return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp, st);
 }
 
 int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype, void *stream) {

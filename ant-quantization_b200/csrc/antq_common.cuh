@@ -38,6 +38,10 @@ struct AntqCodebook {
     float thr[ANTQ_MAX_GRID];           // thr[r] = min{d : level r+1 wins the scan over level r}
     float mag_tpos[ANTQ_MAX_GRID / 2];  // SYMMETRIC: d >= 0 : magnitude k+1 wins iff  d >= mag_tpos[k]
     float mag_tneg[ANTQ_MAX_GRID / 2];  //            d <  0 : magnitude k+1 wins iff -d >= mag_tneg[k]
+    // ANTQ_CB_PU (piecewise-uniform closed form, antq_pu.cu): every level is fl32(k * pu_c) for an integer k in
+    // [pu_kmin, pu_kmax], and inside each octave of |k| the k's form a progression with a power-of-two step.
+    float pu_c, pu_inv_c, pu_kmin, pu_kmax;
+    float2 pu_tab[256];                 // by biased exponent of t = d / pu_c: {1.5 * 2^23 * step, near-midpoint delta}
 };
 
 // ---- total order on fp32 bit patterns (-0 directly below +0) ---------------
@@ -262,3 +266,5 @@ __device__ __forceinline__ float antq_ste_rescale(float q, float d, float s) {
 
 int antq_launch_prepare(const float *grid, int k_normal, const float *outliers, int k_out, AntqCodebook *cb,
                         cudaStream_t stream);
+// SM count of the current device (queried once per device; grids are sized in multiples of it).
+int antq_num_sms();

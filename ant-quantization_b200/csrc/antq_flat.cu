@@ -277,8 +277,9 @@ int antq_launch_absmax(const void *x, float *out, long long rows, long long cols
     if (e != cudaSuccess) return (int)e;
     if (cols == 0) return 0;
     long long splits = 1;
-    if (rows < 148 * 8) {
-        splits = (148 * 8 + rows - 1) / rows;
+    const long long sms = antq_num_sms();
+    if (rows < sms * 8) {
+        splits = (sms * 8 + rows - 1) / rows;
         const long long max_splits = (cols + 2047) / 2048;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
@@ -306,8 +307,9 @@ int antq_launch_mse_sweep(const void *x, const float *base_alpha, int alpha_per_
     if (e != cudaSuccess) return (int)e;
     if (cols == 0) return 0;
     long long chunks = 1;
-    if (rows < 148 * 4) {
-        chunks = (148 * 4 + rows - 1) / rows;
+    const long long sms = antq_num_sms();
+    if (rows < sms * 4) {
+        chunks = (sms * 4 + rows - 1) / rows;
         const long long max_chunks = (cols + 4095) / 4096;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;

@@ -20,6 +20,69 @@ __device__ __forceinline__ bool hi_wins(float d, float lo, float hi, bool tie_hi
     return dh < dl || (dh == dl && tie_hi);
 }
 
+// Piecewise-uniform analysis (one thread; mirrors tests/pu_model.py::analyze line for line).  `ku` is scratch for the
+// union of magnitudes in units of c.  Returns ANTQ_CB_PU (| ANTQ_CB_PU_UNIFORM) and fills the pu_* fields, or 0.
+__device__ int antq_pu_analyze(const float *lev, int L, int *ku, AntqCodebook *cb) {
+    int zero = -1, npos = 0;
+    for (int r = 0; r < L; r++) {
+        if (lev[r] == 0.0f) zero = r;
+        if (lev[r] > 0.0f) npos++;
+    }
+    if (zero < 0 || npos == 0) return 0;
+    const float c = lev[zero + 1];                                   // smallest positive level (levels are sorted, distinct)
+    for (int r = 0; r < L; r++) {
+        const float k = rintf(__fdiv_rn(lev[r], c));
+        if (!(fabsf(k) < 1048576.0f) || __fmul_rn(k, c) != lev[r]) return 0;
+    }
+    const int nneg = zero, np = L - 1 - zero;
+    const float kmin = rintf(__fdiv_rn(lev[0], c)), kmax = rintf(__fdiv_rn(lev[L - 1], c));
+    // the side reaching further defines U; the other side must be a prefix of it
+    const bool pos_longer = kmax >= -kmin;
+    const int nu = pos_longer ? np : nneg, nb = pos_longer ? nneg : np;
+    for (int i = 0; i < nu; i++)
+        ku[i] = (int)rintf(fabsf(__fdiv_rn(pos_longer ? lev[zero + 1 + i] : lev[zero - 1 - i], c)));
+    for (int i = 0; i < nb; i++) {
+        const int kb = (int)rintf(fabsf(__fdiv_rn(pos_longer ? lev[zero - 1 - i] : lev[zero + 1 + i], c)));
+        if (i >= nu || kb != ku[i]) return 0;
+    }
+    if (ku[0] != 1) return 0;
+    int e_top = 0;
+    while ((2 << e_top) <= ku[nu - 1]) e_top++;
+    if (e_top > 30) return 0;
+    int ls[32];
+    int i0 = 0;
+    bool uniform = true;
+    for (int e = 0; e <= e_top; e++) {
+        int n = 0;
+        while (i0 + n < nu && ku[i0 + n] < (2 << e)) n++;
+        if (n == 0 || ku[i0] != (1 << e)) return 0;
+        int step;
+        if (n == 1) step = (e < e_top || e == 0) ? (1 << e) : (1 << ls[e - 1]);
+        else step = ku[i0 + 1] - ku[i0];
+        if (step <= 0 || (step & (step - 1)) || step > (1 << e)) return 0;
+        const int full = (1 << e) / step;
+        if (e < e_top ? n != full : n > full) return 0;
+        for (int j = 0; j < n; j++)
+            if (ku[i0 + j] != (1 << e) + j * step) return 0;
+        int l2 = 0;
+        while ((1 << l2) < step) l2++;
+        ls[e] = l2;
+        if (l2 != 0) uniform = false;
+        i0 += n;
+    }
+    for (int E = 0; E < 256; E++) {
+        int e = E - 127;
+        e = e < 0 ? 0 : (e > e_top ? e_top : e);
+        cb->pu_tab[E] = make_float2(__uint_as_float(((unsigned)(150 + ls[e]) << 23) | 0x400000u),   // 1.5 * 2^(23 + ls)
+                                    __uint_as_float((unsigned)(127 + e - 19) << 23));              // 2^(e - 19)
+    }
+    cb->pu_c = c;
+    cb->pu_inv_c = __fdiv_rn(1.0f, c);
+    cb->pu_kmin = kmin;
+    cb->pu_kmax = kmax;
+    return ANTQ_CB_PU | (uniform ? ANTQ_CB_PU_UNIFORM : 0);
+}
+
 __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float *__restrict__ grid, int k_normal,
                                                                      const float *__restrict__ outliers, int k_out,
                                                                      AntqCodebook *__restrict__ cb) {
@@ -133,6 +196,8 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
         }
         if (ovp_index < 0 && !sym) { /* no outlier level at all: OVP is a no-op */ }
         if (ovp_ok) flags |= ANTQ_CB_OVP_OK;
+        cb->pu_c = 0.0f; cb->pu_inv_c = 0.0f; cb->pu_kmin = 0.0f; cb->pu_kmax = 0.0f;
+        if (sep && ste) flags |= antq_pu_analyze(lev, L, keep, cb);     // keep[] is free by now: scratch
 
         cb->n_entries = K;
         cb->n_normal = k_normal;

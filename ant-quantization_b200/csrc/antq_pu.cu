@@ -1,0 +1,473 @@
+// antq_pu.cu -- closed-form fake-quant for PIECEWISE-UNIFORM codebooks (ANTQ_CB_PU): int-k of every width (the
+// reference forces int above 6 bits, A/antquant/quant_modules.py:482-483), unsigned 4-bit grids (every post-ReLU
+// activation), 5/6-bit flint / pot / float -- everything whose compare chain would be 15 to 255 thresholds long.
+//
+// Same reference arithmetic as the other kernels (A/antquant/quant_modules.py:535-551, A/quant/quant_kernel.cu:25-37):
+//   s = alpha / max(grid);  d = fl32(x / s);  q = scan(d);  out = fl32(((q - d) + d) * s)
+// but the level is found WITHOUT a scan, a chain or a table per row (model + proof by exhaustion: tests/pu_model.py):
+//   t  = x * kx                      kx = fl32(fl32(1 / s) / c), c = the grid's unit: every level is fl32(k c), k integer
+//   mf = (t + M_e) - M_e             M_e = 1.5 * 2^23 * step_e rounds t to the octave's (power-of-two) step
+//   q  = fl32(clamp(mf, kmin, kmax) * c);   out = RN(fl32(q * s))      ((q - d) + d == q inside the window)
+// t is a few ulps off d / c, so an element whose t lies within delta_e = 2^(e - 19) of a midpoint -- or outside the
+// exact window, NaN, Inf, or in a row whose scale is not a positive finite number -- is redone with the literal
+// arithmetic (true division, the codebook's exact thresholds / the literal scan).  With 16-bit data that is ~1e-4 of
+// the elements, except in rows where a tie x / s == midpoint is representable.
+//
+// Two execution shapes:
+//   antq_pu_stream_kernel   rows >= 512 elements / per-tensor: the persistent pipeline of antq_stream.cu (one CTA per
+//                           SM, 12 consumer warps, two private 4 KiB TMA stages each, chunk counter) -- minus the row
+//                           tables, the builder warps and the prologue: a row needs three scalars.
+//   antq_pu_short_kernel    shorter rows and scale groups (group-8/16/32, 1x1-conv weights): grid-stride over 16-byte
+//                           vectors, one IEEE division per VECTOR (for s) instead of one per element.
+// Bound: HBM in principle; ~17 fp32 / integer instructions per element keep the SM's issue slots ~85 % busy at the
+// HBM rate (measured: profiles/r02_notes.md).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "antq_common.cuh"
+
+namespace {
+
+constexpr int kNC = 12;                   // consumer warps per CTA
+constexpr int kNS = 2 * kNC;              // two private stages per warp
+constexpr int kChunkMax = 4096;
+constexpr int kThreads = kNC * 32;
+constexpr unsigned kHalfFromMagic = 0x0C400000u;   // bits(1.5 * 2^k) - bits(2^(k - 24))
+
+struct PuParams {
+    const void *x;
+    void *out;
+    const float *alpha;
+    const AntqCodebook *cb;
+    long long rows, cols;
+    unsigned total_chunks, chunks_per_cta, chunks_rem;
+    int alpha_per_row, chunks_per_row, chunk_elems, cpr_shift;
+    float gmax, lim;
+    int debug;
+    // short kernel
+    unsigned nvec, cols_vec;
+    int cols_shift;
+};
+
+struct PuK {                               // the codebook's closed-form constants (AntqCodebook::pu_*)
+    float c, inv_c, kmin, kmax;
+};
+__device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
+    PuK k;
+    k.c = cb->pu_c; k.inv_c = cb->pu_inv_c; k.kmin = cb->pu_kmin; k.kmax = cb->pu_kmax;
+    return k;
+}
+
+struct PuRow {
+    float s, kx, xl;
+    bool ok;
+};
+
+__device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const PuK &K, bool fast_rcp) {
+    PuRow r;
+    const float inf = __int_as_float(0x7f800000);
+    r.s = __fdiv_rn(alpha, p.gmax);                                   // scale = alpha / max(grid)
+    float rs;
+    if (fast_rcp) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r.s));   // <= 1 ulp: inside delta's budget
+    else rs = __fdiv_rn(1.0f, r.s);
+    r.kx = __fmul_rn(rs, K.inv_c);
+    r.ok = r.s > 0.0f && r.s < inf && r.kx > 0.0f && r.kx < inf;
+    r.xl = __fmul_rn(__fmul_rn(p.lim, r.s), 0.9990234375f);           // conservative exact window in x-space
+    return r;
+}
+
+// The closed form for one element.  `flag` accumulates "redo me exactly".
+template <bool UNIFORM>
+__device__ __forceinline__ float pu_quant(float xf, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
+    const float t = __fmul_rn(xf, r.kx);
+    float M, dl;
+    if (UNIFORM) {
+        M = 12582912.0f;                                              // 1.5 * 2^23: step 1 everywhere
+        dl = fmaxf(__fmul_rn(fabsf(t), 1.9073486328125e-06f), 9.5367431640625e-07f);   // max(|t| 2^-19, 2^-20)
+    } else {
+        const float2 md = tab[__float_as_uint(t) >> 23];              // sign + exponent index a 512-entry table
+        M = md.x; dl = md.y;
+    }
+    const float mf = __fsub_rn(__fadd_rn(t, M), M);
+    const float rr = __fsub_rn(t, mf);                                // exact
+    const float h = UNIFORM ? 0.5f : __uint_as_float(__float_as_uint(M) - kHalfFromMagic);
+    const float v = __fsub_rn(fabsf(rr), h);
+    flag |= fabsf(v) <= dl;
+    const float q = __fmul_rn(fminf(fmaxf(mf, K.kmin), K.kmax), K.c);
+    return __fmul_rn(q, r.s);
+}
+
+// The reference arithmetic for ONE element, literally (exact thresholds inside the proven window, else the scan).
+template <typename T> __device__ __noinline__ T pu_exact_elem(const AntqCodebook *__restrict__ cb, float xf, float s) {
+    const float d = __fdiv_rn(xf, s);
+    float q;
+    if ((cb->flags & ANTQ_CB_WELLSEP) && fabsf(d) <= cb->lim_idx) {
+        q = cb->level[antq_rank(cb->thr, cb->n_levels - 1, d)];
+    } else {
+        int code;
+        q = antq_scan_literal(cb->grid, cb->n_entries, d, code);
+    }
+    return AntqType<T>::from_f32_rn(antq_ste_rescale(q, d, s));
+}
+
+template <typename T> struct PuIO;
+template <> struct PuIO<float> {
+    static constexpr int VEC = 4;
+    __device__ static __forceinline__ void unpack(const uint4 r, float (&f)[4]) {
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    }
+    __device__ static __forceinline__ uint4 pack(const float (&o)[4]) {
+        return make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+    }
+};
+template <> struct PuIO<__half> {
+    static constexpr int VEC = 8;
+    __device__ static __forceinline__ void unpack(const uint4 r, float (&f)[8]) {
+        const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float2 v = __half22float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+    }
+    __device__ static __forceinline__ uint4 pack(const float (&o)[8]) {
+        uint4 q;
+        __half2 *h = reinterpret_cast<__half2 *>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+        return q;
+    }
+};
+template <> struct PuIO<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    __device__ static __forceinline__ void unpack(const uint4 r, float (&f)[8]) {
+        const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+    __device__ static __forceinline__ uint4 pack(const float (&o)[8]) {
+        uint4 q;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        return q;
+    }
+};
+
+// One 16-byte vector through the closed form; `flag` = some element needs the exact redo.
+template <typename T, bool UNIFORM>
+__device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC], o[VEC];
+    PuIO<T>::unpack(raw, f);
+    bool fl = false;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) {
+        o[e] = pu_quant<UNIFORM>(f[e], r, K, tab, fl);
+        fl |= !(fabsf(f[e]) <= r.xl);                                 // outside the exact window, NaN, Inf
+    }
+    flag = fl;
+    return PuIO<T>::pack(o);
+}
+
+// Redo of the flagged elements of one vector (the vector itself has already been stored by this thread).
+template <typename T, bool UNIFORM>
+__device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, const uint4 raw, const PuRow r, const PuK K,
+                                         const float2 *tab, T *og) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC];
+    PuIO<T>::unpack(raw, f);
+#pragma unroll 1
+    for (int e = 0; e < VEC; e++) {
+        bool fl = !r.ok;
+        if (r.ok) {
+            (void)pu_quant<UNIFORM>(f[e], r, K, tab, fl);
+            fl |= !(fabsf(f[e]) <= r.xl);
+        }
+        if (fl) og[e] = pu_exact_elem<T>(cb, f[e], r.s);
+    }
+}
+
+__device__ __forceinline__ void pu_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
+}
+
+// ==================================================================================================
+// Long rows / per-tensor: persistent CTAs, TMA-staged chunks.
+// ==================================================================================================
+template <typename T, bool UNIFORM>
+__global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuParams p) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    extern __shared__ __align__(128) unsigned char pu_smem[];
+    float2 *tab = reinterpret_cast<float2 *>(pu_smem + (size_t)kNS * kChunkMax);          // 512 entries
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 512);
+    unsigned *next_k = reinterpret_cast<unsigned *>(full + kNS);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned c_begin = blockIdx.x * p.chunks_per_cta + min(blockIdx.x, p.chunks_rem);
+    const int n = (int)p.chunks_per_cta + (blockIdx.x < p.chunks_rem ? 1 : 0);
+    const unsigned cpr = (unsigned)p.chunks_per_row;
+    const AntqCodebook *__restrict__ cb = p.cb;
+
+    asm volatile("griddepcontrol.launch_dependents;");                // programmatic dependent launch, as antq_stream.cu
+    if (threadIdx.x < kNS) antq_mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x == 0) *next_k = 0;
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    struct Geo { long long base; int nvec, tail; float alpha; };
+    auto geo_of = [&](int k) {
+        Geo g;
+        const unsigned c = c_begin + (unsigned)k;
+        const unsigned row = p.cpr_shift >= 0 ? c >> p.cpr_shift : c / cpr;
+        const long long col0 = (long long)(c - row * cpr) * p.chunk_elems;
+        const long long remain = p.cols - col0;
+        const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+        g.nvec = n_el / VEC;
+        g.tail = n_el - g.nvec * VEC;
+        g.base = (long long)row * p.cols + col0;
+        g.alpha = 0.0f;
+        return g;
+    };
+    auto request = [&](Geo &g, int stage) {
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)g.nvec * 16u;
+            if (bytes) {
+                antq_fence_proxy_async();
+                antq_bulk_g2s(pu_smem + (size_t)stage * kChunkMax, reinterpret_cast<const T *>(p.x) + g.base, bytes,
+                              full + stage);
+            } else {
+                pu_mbar_arrive(full + stage);
+            }
+        }
+        // the row's alpha travels with the request: its latency hides behind the bulk copy
+        g.alpha = __ldg(p.alpha + (p.alpha_per_row ? (g.base / p.cols) : 0));
+    };
+    auto claim = [&]() {
+        int k = 0;
+        if (lane == 0) k = (int)atomicAdd(next_k, 1u);
+        return __shfl_sync(0xffffffffu, k, 0);
+    };
+
+    Geo cur;
+    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.alpha = 0.0f;
+    int k = claim();
+    if (k < n) {
+        cur = geo_of(k);
+        request(cur, warp);
+    }
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 512; i += kThreads) tab[i] = cb->pu_tab[i & 255];
+    }
+    const PuK K = pu_load_k(cb);
+    __syncthreads();
+
+    int slot = 0;
+    unsigned phases = 0;
+    while (k < n) {
+        const int stage = warp + slot * kNC;
+        const Geo g = cur;
+        const int kn = claim();
+        if (kn < n) {
+            cur = geo_of(kn);
+            request(cur, warp + (slot ^ 1) * kNC);
+        }
+        const PuRow r = pu_row(g.alpha, p, K, false);
+        const int nvec = g.nvec;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(pu_smem + (size_t)stage * kChunkMax);
+        T *og = reinterpret_cast<T *>(p.out) + g.base;
+        uint4 *ov = reinterpret_cast<uint4 *>(og);
+        antq_mbar_wait(full + stage, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        unsigned redo = 0;                                            // bit j: vector j * 32 + lane needs the exact pass
+        if (r.ok && !(p.debug & 2)) {
+            const uint4 *sp = sv + lane;
+            uint4 *op = ov + lane;
+            int j = 0;
+#pragma unroll 1
+            for (int v = lane; v + 32 < nvec; v += 64, j += 2) {
+                const uint4 r0 = sp[0], r1 = sp[32];
+                bool f0, f1;
+                const uint4 q0 = pu_vec<T, UNIFORM>(r0, r, K, tab, f0);
+                const uint4 q1 = pu_vec<T, UNIFORM>(r1, r, K, tab, f1);
+                antq_stg_stream(op, q0);
+                antq_stg_stream(op + 32, q1);
+                redo |= (f0 ? 1u : 0u) << j;
+                redo |= (f1 ? 2u : 0u) << j;
+                sp += 64; op += 64;
+            }
+            if (j * 32 + lane < nvec) {
+                bool f0;
+                const uint4 q0 = pu_vec<T, UNIFORM>(*sp, r, K, tab, f0);
+                antq_stg_stream(op, q0);
+                redo |= (f0 ? 1u : 0u) << j;
+            }
+        } else if (p.debug & 2) {
+            for (int v = lane; v < nvec; v += 32) antq_stg_stream(ov + v, sv[v]);
+        } else {
+            redo = 0xffffffffu;                                       // bad scale: every vector, literally
+        }
+        if (__any_sync(0xffffffffu, redo != 0)) {
+            for (int j = 0; j * 32 + lane < nvec; j++) {
+                if ((redo >> j) & 1u) {
+                    const int v = j * 32 + lane;
+                    pu_redo_vec<T, UNIFORM>(cb, sv[v], r, K, tab, og + (long long)v * VEC);
+                }
+            }
+        }
+        if (g.tail > 0 && lane == 0) {                                 // ragged tail of a per-tensor view
+            const T *xg = reinterpret_cast<const T *>(p.x) + g.base + (long long)nvec * VEC;
+            for (int e = 0; e < g.tail; e++)
+                og[(long long)nvec * VEC + e] = pu_exact_elem<T>(cb, A::to_f32(xg[e]), r.s);
+        }
+        __syncwarp();
+        k = kn;
+        slot ^= 1;
+    }
+}
+
+// ==================================================================================================
+// Short rows / scale groups: grid-stride over 16-byte vectors.
+// ==================================================================================================
+constexpr int kShortThreads = 256;
+
+template <typename T, bool UNIFORM>
+__global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const PuParams p) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    __shared__ float2 tab[512];
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
+        __syncthreads();
+    }
+    const PuK K = pu_load_k(p.cb);
+    const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
+    uint4 *xout = reinterpret_cast<uint4 *>(p.out);
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < p.nvec; v += stride) {
+        const uint4 raw = antq_ldg_stream(xin + v);
+        unsigned row = 0;
+        if (p.alpha_per_row) row = p.cols_shift >= 0 ? v >> p.cols_shift : v / p.cols_vec;
+        const PuRow r = pu_row(__ldg(p.alpha + row), p, K, true);
+        bool flag = true;
+        uint4 q = raw;
+        if (r.ok) q = pu_vec<T, UNIFORM>(raw, r, K, tab, flag);
+        antq_stg_stream(xout + v, q);
+        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+    }
+}
+
+template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
+    auto kernel = antq_pu_stream_kernel<T, UNIFORM>;
+    const int smem = kNS * kChunkMax + 512 * 8 + kNS * 8 + 16;
+    static unsigned long long configured = 0ull;                     // one bit per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 64 || !((configured >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev < 64) configured |= 1ull << dev;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return (int)e;
+}
+
+template <typename T, bool UNIFORM> int launch_short(const PuParams &p, cudaStream_t st) {
+    const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
+    const long long cap = (long long)antq_num_sms() * 8;
+    antq_pu_short_kernel<T, UNIFORM><<<(int)(want < cap ? want : cap), kShortThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+
+
+// Returns ANTQ_ENOTSUP for shapes the persistent kernel does not cover (more than 2^31 chunks).
+int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st) {
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("ANTQ_DEBUG"); dbg = e ? atoi(e) : 0; }
+    PuParams p = {};
+    p.x = x; p.out = out; p.alpha = alpha; p.cb = cb;
+    p.rows = rows; p.cols = cols;
+    int chunk_bytes = kChunkMax;
+    const long long want = (long long)antq_num_sms() * kNC * 2;
+    while (chunk_bytes > 1024) {
+        const long long ce = chunk_bytes / es;
+        if (rows * ((cols + ce - 1) / ce) >= want) break;
+        chunk_bytes >>= 1;
+    }
+    p.chunk_elems = chunk_bytes / es;
+    const long long cpr = (cols + p.chunk_elems - 1) / p.chunk_elems;
+    if (cpr > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    p.chunks_per_row = (int)cpr;
+    p.cpr_shift = -1;
+    if ((cpr & (cpr - 1)) == 0) {
+        int sh = 0;
+        while ((1LL << sh) < cpr) sh++;
+        p.cpr_shift = sh;
+    }
+    const long long total = rows * cpr;
+    if (total == 0) return 0;
+    if (total > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    p.total_chunks = (unsigned)total;
+    p.alpha_per_row = alpha_per_row;
+    p.gmax = info->gmax; p.lim = info->lim;
+    p.debug = dbg;
+    const unsigned sms = (unsigned)antq_num_sms();
+    const int ctas = (int)(p.total_chunks < sms ? p.total_chunks : sms);
+    p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
+    p.chunks_rem = p.total_chunks % (unsigned)ctas;
+    const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
+#define ANTQ_PU_GO(T) (uni ? launch_stream<T, true>(p, ctas, st) : launch_stream<T, false>(p, ctas, st))
+    switch (dtype) {
+        case ANTQ_F32: return ANTQ_PU_GO(float);
+        case ANTQ_F16: return ANTQ_PU_GO(__half);
+        case ANTQ_BF16: return ANTQ_PU_GO(__nv_bfloat16);
+    }
+#undef ANTQ_PU_GO
+    return ANTQ_EINVAL;
+}
+
+int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                         int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st) {
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
+    const int vec = 16 / es;
+    const long long n = rows * cols;
+    if (n == 0) return 0;
+    if (cols % vec || (n / vec) > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    PuParams p = {};
+    p.x = x; p.out = out; p.alpha = alpha; p.cb = cb;
+    p.rows = rows; p.cols = cols;
+    p.nvec = (unsigned)(n / vec);
+    p.cols_vec = (unsigned)(cols / vec);
+    p.cols_shift = -1;
+    if ((p.cols_vec & (p.cols_vec - 1)) == 0) {
+        int sh = 0;
+        while ((1u << sh) < p.cols_vec) sh++;
+        p.cols_shift = sh;
+    }
+    p.alpha_per_row = alpha_per_row;
+    p.gmax = info->gmax; p.lim = info->lim;
+    const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
+#define ANTQ_PU_GO(T) (uni ? launch_short<T, true>(p, st) : launch_short<T, false>(p, st))
+    switch (dtype) {
+        case ANTQ_F32: return ANTQ_PU_GO(float);
+        case ANTQ_F16: return ANTQ_PU_GO(__half);
+        case ANTQ_BF16: return ANTQ_PU_GO(__nv_bfloat16);
+    }
+#undef ANTQ_PU_GO
+    return ANTQ_EINVAL;
+}

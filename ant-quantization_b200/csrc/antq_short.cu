@@ -20,7 +20,6 @@ namespace {
 
 constexpr int kShortThreads = 256;
 constexpr int kShortCtasPerSm = 6;
-constexpr int kNumSms = 148;
 
 struct ShortParams {
     const void *x;
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(kShortThreads, NT <= 7 ? kShortCtasPerSm : 3) 
 
 template <typename T, int NT, bool SYM, bool XNEG, bool OVP> int launch_one(const ShortParams &p, cudaStream_t st) {
     const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
-    const long long cap = (long long)kNumSms * kShortCtasPerSm;
+    const long long cap = (long long)antq_num_sms() * kShortCtasPerSm;
     const int ctas = (int)(want < cap ? want : cap);
     antq_short_kernel<T, NT, SYM, XNEG, OVP><<<ctas, kShortThreads, 0, st>>>(p);
     return (int)cudaGetLastError();

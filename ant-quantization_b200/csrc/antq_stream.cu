@@ -4,7 +4,7 @@
 // calls (A/quant/quant_kernel.cu:11-39): ~9 launches and 7 reads + 7 writes of the tensor become
 // ONE launch, one read, one write.
 //
-// Arithmetic: identical to antq_rows.cu (x-space thresholds, exact STE window; proved bit-exact on
+// Arithmetic: x-space thresholds, exact STE window (proved bit-exact on
 // exhaustive fp16 inputs in tests/test_xspace_model.py).  Per 32-bit register (two 16-bit values):
 //   ALU-pipe chain   m = HSET2.BM(|x| >= X_i);  q ^= m & E_i          (E_i = O_{i+1} xor O_i)
 //   FMA-pipe chain   m = HFMA2.SAT(|x|S, B_i, C_i);  q = HFMA2(m, D_i, q)   (exact, see build_tables)
@@ -12,7 +12,7 @@
 // other cycle, and the scheduler only reaches ~1 instruction/cycle when consecutive instructions of a
 // warp go to different classes (tools/probe/pipe_probe.cu).
 //
-// Execution shape (B200): 148 persistent CTAs, one per SM, each owning an equal contiguous range of
+// Execution shape (B200): one persistent CTA per SM (148 on B200, queried at run time), each owning an equal contiguous range of
 // chunks (<= 4 KiB pieces that never straddle a row) -- found by measurement, profiles/r01_notes.md:
 //   * 12 CONSUMER warps (3 per scheduler).  Each owns two private 4 KiB stages in shared memory and
 //     double-buffers: it claims the next chunk from a CTA-wide counter, puts it in flight with one
@@ -53,7 +53,6 @@ constexpr int kNC = ANTQS_CONSUMERS;      // consumer warps per CTA
 constexpr int kRing = ANTQS_RING;         // private ring stages per consumer warp
 constexpr int kNS = kNC * kRing;          // stages per CTA
 constexpr int kChunkMax = ANTQS_CHUNK;    // bytes of tensor per stage
-constexpr int kNumSms = 148;
 constexpr int kMetaWords = 12;
 constexpr int kNB = ANTQS_BUILDERS;        // table-builder warps per CTA
 constexpr int kThreads = (kNC + kNB) * 32;       // consumers | builders
@@ -1002,7 +1001,7 @@ static unsigned long long *antqs_trace_buffer = nullptr;
 // Tuning builds (-DANTQS_TRACE) record a per-CTA timeline into this device buffer (148 x 264 u64); NULL = off.
 extern "C" void antq_debug_stream_trace(void *device_buffer) { antqs_trace_buffer = (unsigned long long *)device_buffer; }
 
-// Returns ANTQ_ENOTSUP for configurations this kernel does not cover (the caller falls back to antq_rows_kernel).
+// Returns ANTQ_ENOTSUP for configurations this kernel does not cover (the caller falls back to the generic kernel).
 int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                        int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st) {
     const bool symx = (info->flags & ANTQ_CB_SYMX) != 0 && !ovp && !(info->flags & ANTQ_CB_SYMMETRIC);
@@ -1024,7 +1023,7 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     if (chunk_env >= 512 && chunk_env <= kChunkMax && (chunk_env & (chunk_env - 1)) == 0) {
         chunk_bytes = chunk_env;
     } else {
-        const long long want = (long long)kNumSms * kNC * 2;
+        const long long want = (long long)antq_num_sms() * kNC * 2;
         while (chunk_bytes > 1024) {
             const long long ce = chunk_bytes / es;
             if (rows * ((cols + ce - 1) / ce) >= want) break;
@@ -1050,7 +1049,8 @@ int antq_launch_stream(const void *x, void *out, const float *alpha, int alpha_p
     p.gmax = info->gmax; p.lim = info->lim;
     p.debug = dbg;
     p.trace = antqs_trace_buffer;
-    const int ctas = (int)(p.total_chunks < (unsigned)kNumSms ? p.total_chunks : (unsigned)kNumSms);
+    const unsigned sms = (unsigned)antq_num_sms();
+    const int ctas = (int)(p.total_chunks < sms ? p.total_chunks : sms);
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
     p.chunks_rem = p.total_chunks % (unsigned)ctas;
     if (symx) {

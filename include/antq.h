@@ -50,7 +50,9 @@ extern "C" {
 /* flags for antq_fakequant */
 #define ANTQ_FLAG_OVP        1      /* OliVe outlier-victim pair masking on the flat tensor */
 #define ANTQ_FLAG_FORCE_FLAT 2      /* testing: always take the generic flat kernel */
-#define ANTQ_FLAG_FORCE_ROWS 4      /* testing: fail (ANTQ_ENOTSUP) instead of falling back */
+#define ANTQ_FLAG_FORCE_ROWS 4      /* testing: the row-table kernel (plan 1) or fail with ANTQ_ENOTSUP */
+#define ANTQ_FLAG_FORCE_PU   8      /* testing: the closed-form kernels (plans 4 / 5) or fail with ANTQ_ENOTSUP */
+#define ANTQ_FLAG_NO_PU     16      /* testing / A-B: never take the closed-form kernels */
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define ANTQ_EINVAL  (-1)
@@ -95,6 +97,9 @@ int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, 
 #define ANTQ_CB_OVP_OK    8   /* no outlier level (|v| > 32) on the negative side of an asymmetric grid */
 #define ANTQ_CB_SYMX     16   /* symmetric about zero except for one extra level at the negative end (signed int-k);
                                  n_mag = magnitudes present on both sides, mid = index of the zero level */
+#define ANTQ_CB_PU       32   /* piecewise uniform: levels are fl32(k * c), k integer, power-of-two step per octave
+                                 (int / flint / pot / float of every width): the closed-form kernels apply */
+#define ANTQ_CB_PU_UNIFORM 64 /* PU with one step for every octave (int-k) */
 
 /* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
  * `info` (host pointer, may be NULL) lets the call pick the row-table kernel
@@ -104,9 +109,11 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
                    const antq_codebook_info *info, int flags, void *stream);
 
 /* Which kernel antq_fakequant launches for these arguments:
- * 1 = row-table kernels (x-space thresholds: antq_stream_kernel, antq_rows_kernel when codes are requested),
- * 3 = short-row / scale-group kernel (d-space threshold chain, rows shorter than 512 elements),
- * 2 = flat generic kernel, <0 = error. */
+ * 1 = antq_stream_kernel (per-row x-space threshold chain; <= 7 thresholds after folding signs, OliVe),
+ * 4 = antq_pu_stream_kernel (closed form for piecewise-uniform grids: unsigned 4-bit, 5 to 8 bit),
+ * 5 = antq_pu_short_kernel (the same for rows shorter than 512 elements: scale groups, 1x1-conv weights),
+ * 3 = antq_short_kernel (d-space threshold chain, short rows of the grids that are not piecewise uniform),
+ * 2 = antq_flat_kernel (generic; the one that emits int16 code indices), <0 = error. */
 int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t cols, int dtype, int flags,
                         const void *x, const void *out, const void *codes);
 

@@ -40,6 +40,15 @@ def test_abi_basics_without_gpu():
     assert _lib.lib.antq_fakequant_plan(ctypes.byref(info), 4096, 4097, _lib.F16, _lib.FLAG_FORCE_ROWS, 256, 512,
                                         None) == _lib.ENOTSUP
     assert _lib.lib.antq_fakequant_plan(None, 4096, 4096, _lib.F16, 0, 256, 512, None) == 2
+    # piecewise-uniform grids: chain up to 7 folded thresholds, closed form beyond and for short rows
+    pu7 = _lib.CodebookInfo(n_entries=16, n_normal=16, n_levels=15, flags=7 | _lib.CB_PU, n_mag=8, mid=7, ovp_index=-1)
+    pu127 = _lib.CodebookInfo(n_entries=256, n_normal=256, n_levels=256, flags=3 | _lib.CB_SYMX | _lib.CB_PU | _lib.CB_PU_UNIFORM,
+                              n_mag=128, mid=128, ovp_index=-1)
+    plan = lambda info, r, c, fl=0, codes=None: _lib.lib.antq_fakequant_plan(ctypes.byref(info), r, c, _lib.F16, fl, 256, 512, codes)
+    assert plan(pu7, 4096, 4096) == 1 and plan(pu7, 4096, 64) == 5 and plan(pu7, 4096, 64, _lib.FLAG_NO_PU) == 3
+    assert plan(pu127, 4096, 4096) == 4 and plan(pu127, 1, 12345) == 4 and plan(pu127, 4096, 32) == 5
+    assert plan(pu127, 4096, 4096, _lib.FLAG_NO_PU) == 2 and plan(pu127, 4096, 4096, 0, 1024) == 2
+    assert plan(pu7, 4096, 4096, _lib.FLAG_FORCE_PU) == 4 and plan(pu7, 4096, 4096, _lib.FLAG_OVP | _lib.FLAG_FORCE_PU) == _lib.ENOTSUP
 
 
 def test_product_never_imports_oracle():

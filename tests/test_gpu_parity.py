@@ -105,11 +105,13 @@ def _run_ant(antq, x_np, alpha_np, grid_np, per_row, flags=0, want_codes=False):
     cb = _cb(antq, grid_np)
     x = torch.from_numpy(x_np).to(dev())
     a = torch.from_numpy(np.ascontiguousarray(alpha_np, dtype=np.float32)).to(dev())
-    r = antq.fakequant(x, a, cb, per_row, want_codes=want_codes, flags=flags)
+    r = antq.fakequant(x, a, cb, per_row, flags=flags)
     if want_codes:
-        # codes come from antq_rows_kernel; the same call without codes takes antq_stream_kernel: both are checked
-        assert_bit_equal(to_np(antq.fakequant(x, a, cb, per_row, flags=flags)), to_np(r[0]), "no-codes vs codes path")
-        return to_np(r[0]), to_np(r[1]).astype(np.int32)
+        # int16 code indices come from the generic kernel; its values must equal the requested kernel's
+        from antq import _lib
+        yf, c = antq.fakequant(x, a, cb, per_row, want_codes=True, flags=_lib.FLAG_FORCE_FLAT)
+        assert_bit_equal(to_np(yf), to_np(r), "generic (codes) path vs requested path")
+        return to_np(r), to_np(c).astype(np.int32)
     return to_np(r)
 
 
@@ -142,11 +144,12 @@ def _run_olive(antq, x_np, alpha_np, grid_np, outl_np, per_row, no_outlier, flag
     cb = _cb(antq, grid_np, None if no_outlier else outl_np)
     x = torch.from_numpy(x_np).to(dev())
     a = torch.from_numpy(np.ascontiguousarray(alpha_np, dtype=np.float32)).to(dev())
-    r = antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, want_codes=want_codes, flags=flags)
+    r = antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, flags=flags)
     if want_codes:
-        assert_bit_equal(to_np(antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, flags=flags)), to_np(r[0]),
-                         "no-codes vs codes path")
-        return to_np(r[0]), to_np(r[1]).astype(np.int32)
+        from antq import _lib
+        yf, c = antq.fakequant(x, a, cb, per_row, ovp=not no_outlier, want_codes=True, flags=_lib.FLAG_FORCE_FLAT)
+        assert_bit_equal(to_np(yf), to_np(r), "generic (codes) path vs requested path")
+        return to_np(r), to_np(c).astype(np.int32)
     return to_np(r)
 
 
@@ -364,9 +367,13 @@ def test_stream_kernel_signed_int(antq, bit, dtype):
     if dtype == "f16":
         x = x.astype(np.float16)
     ref = orc.ant_forward(x, alpha, grid, per_row=True)
-    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True) == 1
+    # up to 7 thresholds after folding signs the chain is the default; beyond, the closed form (plan 4) is, and
+    # FORCE_ROWS still runs the chain
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True) == (1 if bit <= 4 else 4)
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True, flags=_lib.FLAG_FORCE_ROWS) == 1
     y = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_ROWS)
     assert_bit_equal(y, ref, "signed int-%d %s" % (bit, dtype))
+    assert_bit_equal(_run_ant(antq, x, alpha, grid, True, 0), ref, "signed int-%d %s default plan" % (bit, dtype))
     yt = _run_ant(antq, x.reshape(-1), np.float32(alpha.mean()), grid, False, _lib.FLAG_FORCE_ROWS)
     assert_bit_equal(yt, orc.ant_forward(x.reshape(-1), np.float32(alpha.mean()), grid, per_row=False), "per-tensor")
 
@@ -459,8 +466,9 @@ def test_stream_kernel_dependent_launches(antq):
                                                   ("flint", 4, False, 64), ("int", 4, False, 256), ("float2", 4, True, 128),
                                                   ("int", 5, True, 32), ("flint", 3, True, 504), ("int", 3, False, 40)])
 def test_short_rows_and_scale_groups(antq, kind, bit, signed, cols, dtype):
-    """Rows shorter than 512 elements (group-8/16/32 scales, 1x1-conv weights) take antq_short_kernel (plan 3):
-    bit-exact against the oracle and the generic flat kernel, including clipped / NaN / Inf inputs and dead rows."""
+    """Rows shorter than 512 elements (group-8/16/32 scales, 1x1-conv weights) take the closed-form short kernel
+    (plan 5) when the grid is piecewise uniform and the d-space chain kernel (plan 3, here forced with NO_PU) otherwise:
+    both bit-exact against the oracle and the generic flat kernel, including clipped / NaN / Inf inputs and dead rows."""
     from antq import _lib
     rng = np.random.default_rng(cols * 31 + bit)
     grid = orc.ant_grid(kind, bit, signed)
@@ -477,10 +485,13 @@ def test_short_rows_and_scale_groups(antq, kind, bit, signed, cols, dtype):
         x = x.astype(np.float16)
     cb = _cb(antq, grid)
     xd = torch.from_numpy(x).to(dev())
-    assert antq.fakequant_plan(xd, cb, True) == 3
+    assert antq.fakequant_plan(xd, cb, True) == 5
+    assert antq.fakequant_plan(xd, cb, True, flags=_lib.FLAG_NO_PU) == 3
     ref = orc.ant_forward(x, alpha, grid, per_row=True)
     y = _run_ant(antq, x, alpha, grid, True, 0)
-    assert_bit_equal(y, ref, "short kernel %s-%d cols=%d %s" % (kind, bit, cols, dtype))
+    assert_bit_equal(y, ref, "closed-form short kernel %s-%d cols=%d %s" % (kind, bit, cols, dtype))
+    y = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_NO_PU)
+    assert_bit_equal(y, ref, "d-space short kernel %s-%d cols=%d %s" % (kind, bit, cols, dtype))
     yf = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_FLAT)
     assert_bit_equal(yf, ref, "flat kernel")
     antq.fakequant(xd, torch.from_numpy(alpha).to(dev()), cb, True, out=xd)

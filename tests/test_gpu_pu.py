@@ -1,0 +1,158 @@
+"""GPU parity of the closed-form (piecewise-uniform) kernels, antq_pu_stream_kernel / antq_pu_short_kernel, against the
+oracle: every fp16 bit pattern x 16 scales for every grid family they serve (int 3..8 bit, unsigned 4-bit, 5/6-bit
+flint / pot / float), random fp32 / fp16 / bf16 with NaN / Inf / dead rows / representable ties / ragged tails, and the
+codebook analysis itself against tests/pu_model.py (whose arithmetic the CPU suite checks exhaustively)."""
+import numpy as np
+import pytest
+import torch
+
+import antq_oracle as orc
+import pu_model as pm
+from gpu_util import assert_bit_equal, dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+SCALES = [0.1, 1.0, 0.5, 2.0 ** -7, 3.0, 1e-3, 7.7e-3, 250.0, 6e-6, 1.0 / 3.0, 0.0123, 0.37, 2.5e-2, 1.7e-4, 9.0, 41.0]
+PU_GRIDS = [("int", b, sg) for b in (3, 4, 5, 6, 7, 8) for sg in (True, False)]
+PU_GRIDS += [("flint", b, sg) for b in (4, 5, 6) for sg in (True, False)]
+PU_GRIDS += [("pot", 4, True), ("pot", 4, False), ("float2", 4, False), ("float3", 6, True), ("float3", 5, False)]
+
+
+@pytest.fixture(scope="module")
+def antq():
+    import antq as m
+    return m
+
+
+def _cb(antq, grid, outl=None):
+    return antq.prepare_codebook(torch.from_numpy(np.asarray(grid, dtype=np.float32)).to(dev()),
+                                 None if outl is None else torch.from_numpy(np.asarray(outl, dtype=np.float32)).to(dev()))
+
+
+def _run(antq, x_np, alpha_np, cb, per_row, flags):
+    x = x_np if isinstance(x_np, torch.Tensor) else torch.from_numpy(x_np)
+    a = torch.from_numpy(np.ascontiguousarray(alpha_np, dtype=np.float32)).reshape(-1).to(dev())
+    return antq.fakequant(x.to(dev()), a, cb, per_row, flags=flags)
+
+
+def test_codebook_analysis_matches_model(antq):
+    from antq import _lib
+    cases = [(orc.ant_grid(k, b, s), "%s-%d-%s" % (k, b, s)) for k, b, s in PU_GRIDS]
+    cases += [(orc.ant_grid("apot", 4, False), "apot-u"), (orc.ant_grid("apot", 4, True), "apot-s"),
+              (np.concatenate([orc.olive_int_grid(4, True), orc.olive_outlier_grid(4, True)]), "olive int+abfloat"),
+              (orc.olive_flint_grid(4, True), "olive flint"), (orc.olive_int_grid(4, False), "olive int u")]
+    for grid, name in cases:
+        info = _cb(antq, grid).info
+        model = pm.analyze(grid)
+        assert bool(info.flags & _lib.CB_PU) == (model is not None), name
+        if model is not None:
+            assert bool(info.flags & _lib.CB_PU_UNIFORM) == model["uniform"], name
+
+
+@pytest.mark.parametrize("kind,bit,signed", PU_GRIDS)
+def test_pu_exhaustive_fp16(antq, kind, bit, signed):
+    """Every fp16 bit pattern x 16 scales through the closed form: one 65536-element row per scale (stream kernel), and
+    the same data as 64-element rows (short kernel: one scale per 64 elements)."""
+    from antq import _lib
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = _cb(antq, grid)
+    allh = np.arange(65536, dtype=np.uint16).view(np.float16)
+    x = np.tile(allh, (len(SCALES), 1))
+    alpha = (np.array(SCALES, dtype=np.float32) * grid.max()).astype(np.float32)
+    ref = orc.ant_forward(x, alpha, grid, per_row=True)
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True, flags=_lib.FLAG_FORCE_PU) == 4
+    y = _run(antq, x, alpha, cb, True, _lib.FLAG_FORCE_PU)
+    assert_bit_equal(to_np(y), ref, "stream")
+    xs = x.reshape(-1, 64)
+    assert antq.fakequant_plan(torch.from_numpy(xs).to(dev()), cb, True, flags=_lib.FLAG_FORCE_PU) == 5
+    ys = _run(antq, xs, np.repeat(alpha, 65536 // 64), cb, True, _lib.FLAG_FORCE_PU)
+    assert_bit_equal(to_np(ys).reshape(x.shape), ref, "short")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("kind,bit,signed", [("int", 8, True), ("int", 8, False), ("int", 6, True), ("flint", 4, False),
+                                             ("flint", 6, False), ("flint", 5, True), ("pot", 4, False), ("int", 4, True)])
+def test_pu_random(antq, kind, bit, signed, dtype):
+    from antq import _lib
+    rng = np.random.default_rng(17 + bit)
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = _cb(antq, grid)
+    rows, cols = 96, 4096
+    x = (rng.standard_normal((rows, cols)) * 0.02).astype(np.float32)
+    x[rng.integers(0, rows, 50), rng.integers(0, cols, 50)] *= 30          # far outside the clip window
+    x[5, 7], x[9, 100], x[11, 4095] = np.nan, np.inf, -np.inf
+    x[20] = 0.0                                                           # alpha = 0 row -> NaN in the reference
+    if not signed:
+        x = np.abs(x)
+    alpha = (np.abs(np.nan_to_num(x, nan=0, posinf=0, neginf=0)).max(1) * rng.uniform(0.5, 1.2, rows)).astype(np.float32)
+    alpha[3] = np.float32(0.625 * 0.02)                                   # scales that make exact ties representable
+    alpha[::7] = np.float32(0.05 * grid.max() / 8)
+    alpha[40] = -1.0                                                      # a negative scale: literal arithmetic
+    if dtype == "bf16":
+        xt = torch.from_numpy(x).to(torch.bfloat16)
+        ref = torch.from_numpy(orc.ant_forward(xt.float().numpy(), alpha, grid, per_row=True)).to(torch.bfloat16)
+        for shape in ((rows, cols), (rows * cols // 32, 32)):
+            a = alpha if shape[0] == rows else np.repeat(alpha, cols // 32)
+            y = _run(antq, xt.reshape(shape), a, cb, True, _lib.FLAG_FORCE_PU)
+            same = (y.cpu().view(torch.int16) == ref.reshape(shape).view(torch.int16)) | (y.cpu().isnan() & ref.reshape(shape).isnan())
+            assert bool(same.all()), (shape, int((~same).sum()))
+        return
+    if dtype == "f16":
+        x = x.astype(np.float16)
+    ref = orc.ant_forward(x, alpha, grid, per_row=True)
+    assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, _lib.FLAG_FORCE_PU)), ref, "stream per-row")
+    assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, _lib.FLAG_FORCE_FLAT)), ref, "flat per-row")
+    # scale groups of 8 / 32 / 128 elements: the short kernel
+    for g in (8, 32, 128):
+        xs = x.reshape(-1, g)
+        a = np.repeat(alpha, cols // g)
+        assert antq.fakequant_plan(torch.from_numpy(xs).to(dev()), cb, True) == 5
+        assert_bit_equal(to_np(_run(antq, xs, a, cb, True, 0)).reshape(x.shape), ref, "short g=%d" % g)
+    # per-tensor, ragged length: the tail goes through the literal path
+    xt = x.reshape(-1)[: rows * cols - 3]
+    fin = np.isfinite(xt.astype(np.float32))
+    a0 = np.float32(np.abs(xt[fin].astype(np.float32)).max() * 0.9)
+    assert_bit_equal(to_np(_run(antq, xt, a0, cb, False, _lib.FLAG_FORCE_PU)),
+                     orc.ant_forward(xt, a0, grid, per_row=False), "per-tensor ragged")
+    # in place
+    xd = torch.from_numpy(x).to(dev())
+    antq.fakequant(xd, torch.from_numpy(alpha).to(dev()), cb, True, out=xd, flags=_lib.FLAG_FORCE_PU)
+    assert_bit_equal(to_np(xd), ref, "in place")
+
+
+def test_default_plans(antq):
+    """What a model actually hits: 8-bit int weights and post-ReLU 4-bit activations take the closed form, signed 4-bit
+    keeps the chain, OliVe keeps its two-phase chain."""
+    x = torch.zeros(4096, 4096, dtype=torch.float16, device=dev())
+    plan = lambda grid, per_row, outl=None, ovp=False, t=x: antq.fakequant_plan(t, _cb(antq, grid, outl), per_row, ovp=ovp)
+    assert plan(orc.ant_grid("int", 8, True), True) == 4
+    assert plan(orc.ant_grid("int", 8, False), False) == 4
+    assert plan(orc.ant_grid("flint", 4, False), False) == 4
+    assert plan(orc.ant_grid("flint", 6, False), False) == 4
+    assert plan(orc.ant_grid("flint", 4, True), True) == 1
+    assert plan(orc.ant_grid("int", 4, True), True) == 1
+    assert plan(orc.olive_grid("flint", 4, True), True, orc.olive_outlier_grid(4, True), True) == 1
+    assert plan(orc.ant_grid("int", 8, True), True, t=x.view(-1, 64)) == 5
+    assert plan(orc.ant_grid("apot", 4, False), True, t=x.view(-1, 64)) == 3
+
+
+def test_pu_headline_sizes_against_flat(antq):
+    """4096 x 4096 and a 16384-row tensor: closed form == generic kernel everywhere (fp16, int-8 and unsigned flint-4)."""
+    from antq import _lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for kind, bit, signed, shape in (("int", 8, True, (4096, 4096)), ("flint", 4, False, (4096, 4096)),
+                                     ("int", 8, True, (16384, 4096))):
+        grid = orc.ant_grid(kind, bit, signed)
+        cb = _cb(antq, grid)
+        x = (torch.randn(*shape, device=dev(), generator=g) * 0.03).to(torch.float16)
+        if not signed:
+            x = x.abs()
+        x[::97, ::13] *= 40
+        alpha = (x.float().abs().amax(1) * 0.8).contiguous()
+        y = antq.fakequant(x, alpha, cb, True)
+        yf = antq.fakequant(x, alpha, cb, True, flags=_lib.FLAG_FORCE_FLAT)
+        assert torch.equal(y.view(torch.int16), yf.view(torch.int16)), (kind, bit, shape)
+        a0 = alpha.mean().reshape(1)
+        y = antq.fakequant(x, a0, cb, False)
+        yf = antq.fakequant(x, a0, cb, False, flags=_lib.FLAG_FORCE_FLAT)
+        assert torch.equal(y.view(torch.int16), yf.view(torch.int16)), (kind, bit, shape, "per-tensor")

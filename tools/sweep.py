@@ -1,0 +1,132 @@
+"""BASELINE.json config C5, reproducible: synthetic N x N sweep (1k .. 16k) x numeric type (int / pot / flint /
+float / OliVe int+abfloat / OliVe flint+abfloat) x scale granularity (per-tensor, per-row, group-8/16/32) x dtype,
+kernel-only time of antq.fakequant (CUDA graph of `nb` launches over rotating buffer pairs larger than L2, CUDA events).
+
+    python tools/sweep.py [--quick] [--out gpurun_out/r02_sweep.jsonl]
+
+One JSON line per case: plan (which kernel), us per launch, algorithmic GB/s (sizeof(in) + sizeof(out) per element,
+SURVEY.md 8(d)) and the fraction of the measured HBM peak (MEASURED_PEAKS.json, else the profiling guide's fallback).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ant-quantization_b200"))
+import torch  # noqa: E402
+import antq  # noqa: E402
+from antq import _lib, codebooks  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def time_graph(step, reps):
+    step(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20):
+    dev = torch.device("cuda:0")
+    dt = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[dtype]
+    es = 4 if dtype == "f32" else 2
+    pair = n * n * es * 2
+    nb = max(2, min(16, -(-(300 << 20) // pair)))                     # rotate > 126 MB L2
+    if olive:
+        cb = antq.prepare_codebook(codebooks.olive_grid(kind, bit, signed).to(dev), codebooks.olive_outliers(bit, signed).to(dev))
+    else:
+        cb = antq.prepare_codebook(codebooks.ant_grid(kind, bit, signed).to(dev))
+    g = torch.Generator(device="cuda").manual_seed(n + bit)
+    xs, als, outs = [], [], []
+    for _ in range(nb):
+        x = torch.randn(n, n, device=dev, generator=g) * 0.02
+        if not signed:
+            x = x.abs()
+        x = x.to(dt)
+        if gran == "tensor":
+            v, per_row = x, False
+            al = x.float().abs().max().reshape(1) * 0.9
+        else:
+            gsz = n if gran == "row" else int(gran[1:])
+            v, per_row = x.view(-1, gsz), True
+            al = v.float().abs().amax(1) * 0.9
+        if olive:
+            al = torch.full_like(al, float(3 * x.float().std()))
+        xs.append(v); als.append(al.contiguous()); outs.append(torch.empty_like(v))
+    plan = antq.fakequant_plan(xs[0], cb, per_row, ovp=olive, flags=flags)
+
+    def step():
+        for i in range(nb):
+            antq.fakequant(xs[i], als[i], cb, per_row, ovp=olive, out=outs[i], flags=flags)
+    us = time_graph(step, reps) / nb
+    pk, src = peak()
+    gbs = n * n * es * 2 / us / 1e3
+    return {"n": n, "type": ("olive-" if olive else "") + kind, "bit": bit, "signed": signed, "granularity": gran,
+            "dtype": dtype, "plan": plan, "us": round(us, 2), "GBps": round(gbs, 1), "frac": round(gbs / pk, 3),
+            "peak": pk, "peak_source": src, "nb": nb}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_sweep.jsonl"))
+    a = ap.parse_args()
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    sizes = [1024, 2048, 4096, 8192, 16384]
+    types = [("int", 4, True, False), ("pot", 4, True, False), ("flint", 4, True, False), ("float2", 4, True, False),
+             ("flint", 4, False, False), ("int", 4, False, False), ("int", 8, True, False), ("int", 8, False, False),
+             ("int", 6, True, False), ("flint", 6, False, False), ("flint", 5, True, False),
+             ("int", 4, True, True), ("flint", 4, True, True), ("flint", 4, False, True)]
+    grans = ["tensor", "row", "g8", "g16", "g32"]
+    rows = []
+    with open(a.out, "w") as f:
+        def emit(r):
+            rows.append(r)
+            f.write(json.dumps(r) + "\n"); f.flush()
+            print(json.dumps(r), flush=True)
+        if a.quick:
+            for t in types:
+                emit(case(4096, *t, "row", "f16"))
+            return
+        # every type x granularity at the headline size, fp16
+        for t in types:
+            for gr in grans:
+                emit(case(4096, *t, gr, "f16"))
+        # size sweep, per-row and per-tensor, the three headline types
+        for n in sizes:
+            if n == 4096:
+                continue
+            for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False), ("flint", 4, True, True)):
+                for gr in ("row", "tensor", "g32"):
+                    emit(case(n, *t, gr, "f16", reps=10 if n >= 8192 else 20))
+        # dtypes
+        for dt in ("f32", "bf16"):
+            for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False)):
+                for gr in ("row", "g32"):
+                    emit(case(4096, *t, gr, dt))
+        # A/B: what the closed form replaced (chain / generic kernel on the same cases)
+        for t in (("int", 8, True, False), ("flint", 4, False, False), ("int", 6, True, False), ("flint", 5, True, False)):
+            for gr in ("row", "g32"):
+                r = case(4096, *t, gr, "f16", flags=_lib.FLAG_NO_PU)
+                r["note"] = "NO_PU (round-1 path)"
+                emit(r)
+
+
+if __name__ == "__main__":
+    main()
