@@ -55,6 +55,16 @@ def _load():
     L.antq_fakequant_plan.argtypes = [ip, i64, i64, ci, ci, vp, vp, vp]
     L.antq_absmax.argtypes = [vp, vp, i64, i64, ci, vp]
     L.antq_mse_sweep.argtypes = [vp, vp, ci, vp, ci, vp, i64, i64, ci, vp, ci, vp]
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    L.antq_encode_p4.argtypes = [vp, vp, vp, ci, i64, i64, ci, vp, ip, ci, vp, vp]
+    L.antq_decode_p4.argtypes = [vp, vp, vp, ci, i64, i64, ci, vp, ip, ci, vp]
+    L.antq_backward_workspace_bytes.argtypes = [i64, i64, ci]
+    L.antq_backward_workspace_bytes.restype = sz
+    L.antq_fakequant_backward.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, ctypes.c_float, vp, vp, vp, sz, vp]
+    L.antq_calibrate_workspace_bytes.argtypes = [i64, i64, ci, ci, ci]
+    L.antq_calibrate_workspace_bytes.restype = sz
+    L.antq_calibrate.argtypes = [vp, i64, i64, ci, ci, vp, vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ip), ctypes.POINTER(ci),
+                                 ci, vp, vp, vp, vp, sz, vp]
     L.antq_host_create.argtypes = [ctypes.POINTER(vp), ci, sz, ci]
     L.antq_host_destroy.argtypes = [vp]
     L.antq_host_destroy.restype = None
@@ -64,7 +74,8 @@ def _load():
     L.antq_host_last_launches.argtypes = [vp]
     for name in ("antq_codebook_prepare", "antq_codebook_info_get", "antq_lut_nearest", "antq_fakequant",
                  "antq_fakequant_plan", "antq_absmax", "antq_mse_sweep", "antq_host_create",
-                 "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches"):
+                 "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches",
+                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate"):
         getattr(L, name).restype = ci
     return L
 

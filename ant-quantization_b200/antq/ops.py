@@ -163,7 +163,7 @@ def fakequant(x, alpha, cb, per_row, ovp=False, want_codes=False, flags=0, out=N
         codes = torch.empty(x.shape, dtype=torch.int16, device=dev) if want_codes else None
         fl = flags | (_lib.FLAG_OVP if ovp else 0)
         rc = _antq_fakequant(x.data_ptr(), out.data_ptr(), codes.data_ptr() if want_codes else None,
-                             a.data_ptr(), 1 if per_row else 0, rows, cols, _DT[x.dtype], cb.ptr,
+                             a.data_ptr(), 1 if per_row else 0, rows, cols, _dtype_code(x), cb.ptr,
                              cb.info_ref, fl, _raw_stream(dev.index))
         if rc:
             check(rc, "antq_fakequant")
@@ -220,6 +220,93 @@ def mse_sweep(x, base_alpha, ratios, cb, per_row, ovp=False):
                                  _dtype_code(xc), _ptr(cb.buf), _lib.FLAG_OVP if ovp else 0, _stream()),
               "antq_mse_sweep")
     return err
+
+
+def encode_p4(x, alpha, cb, per_row, ovp=False, count_inexact=True):
+    """Packed 4-bit codes of the fake-quantized tensor (include/antq.h: antq_encode_p4).  Returns (codes, n_inexact):
+    codes is a uint8 tensor of numel / 2 bytes (row-major, low nibble = even element); n_inexact a 1-element int32
+    device tensor (None if not requested) counting the elements decode_p4 would not reproduce bit for bit."""
+    _need_cuda(x, "x")
+    if not x.is_contiguous():
+        raise RuntimeError("antq: x must be contiguous")
+    with _maybe_guard(x.device):
+        rows, cols = _rows_cols(x, per_row)
+        a = _alpha_arg(alpha, rows, per_row, x.device)
+        codes = torch.empty(x.numel() // 2, dtype=torch.uint8, device=x.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=x.device) if count_inexact else None
+        check(lib.antq_encode_p4(_ptr(x), _ptr(codes), _ptr(a), int(bool(per_row)), rows, cols, _dtype_code(x), cb.ptr,
+                                 cb.info_ref, _lib.FLAG_OVP if ovp else 0, _ptr(cnt), _stream()), "antq_encode_p4")
+    return codes, cnt
+
+
+def decode_p4(codes, alpha, cb, shape, dtype, per_row, ovp=False, out=None):
+    """values = level[code] * (alpha / max(grid)), rounded to `dtype` (antq_decode_p4)."""
+    _need_cuda(codes, "codes")
+    shape = tuple(shape)
+    n = 1
+    for d in shape:
+        n *= d
+    if codes.dtype is not torch.uint8 or codes.numel() * 2 != n or not codes.is_contiguous():
+        raise ValueError("antq: codes must be a contiguous uint8 tensor of numel / 2 bytes")
+    with _maybe_guard(codes.device):
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=codes.device)
+        elif not (out.dtype is dtype and out.device == codes.device and out.numel() == n and out.is_contiguous()):
+            raise ValueError("antq: `out` must be a contiguous %s tensor with %d elements on %s" % (dtype, n, codes.device))
+        rows, cols = _rows_cols(out.view(shape), per_row)
+        a = _alpha_arg(alpha, rows, per_row, codes.device)
+        check(lib.antq_decode_p4(_ptr(codes), _ptr(out), _ptr(a), int(bool(per_row)), rows, cols, _dtype_code(out), cb.ptr,
+                                 cb.info_ref, _lib.FLAG_OVP if ovp else 0, _stream()), "antq_decode_p4")
+    return out
+
+
+def fakequant_backward(grad_out, x, out, alpha, gmax, per_row, need_grad_x=True, need_grad_alpha=True):
+    """QAT backward of the fused forward in one pass (antq_fakequant_backward): returns (grad_x, grad_alpha[fp32])."""
+    _need_cuda(grad_out, "grad_out")
+    with _maybe_guard(x.device):
+        g = grad_out if grad_out.is_contiguous() else grad_out.contiguous()
+        if g.dtype is not x.dtype:
+            g = g.to(x.dtype)
+        xc = x if x.is_contiguous() else x.contiguous()
+        oc = out if out.is_contiguous() else out.contiguous()
+        rows, cols = _rows_cols(xc, per_row)
+        a = _alpha_arg(alpha, rows, per_row, x.device)
+        gx = torch.empty_like(xc) if need_grad_x else None
+        ga = ws = None
+        nws = 0
+        if need_grad_alpha:
+            ga = torch.empty(rows if per_row else 1, dtype=torch.float32, device=x.device)
+            nws = lib.antq_backward_workspace_bytes(rows, cols, int(bool(per_row)))
+            ws = torch.empty(max(nws, 8), dtype=torch.uint8, device=x.device)
+        check(lib.antq_fakequant_backward(_ptr(g), _ptr(xc), _ptr(oc), _ptr(a), int(bool(per_row)), rows, cols,
+                                          _dtype_code(xc), float(gmax), _ptr(gx), _ptr(ga), _ptr(ws), nws, _stream()),
+              "antq_fakequant_backward")
+    return gx, ga
+
+
+def calibrate(x, base_alpha, ratios, cbs, per_row, ovp=False, want_index=False):
+    """Fused calibration (antq_calibrate): every candidate alpha = base * ratio of every codebook in `cbs` scored in
+    one read of x.  Returns (alpha[n_cb, rows], mse[n_cb][, best_index[n_cb, rows]]) -- device tensors, no host sync."""
+    _need_cuda(x, "x")
+    with _maybe_guard(x.device):
+        xc = x if x.is_contiguous() else x.contiguous()
+        rows, cols = _rows_cols(xc, per_row)
+        base = _alpha_arg(base_alpha, rows, per_row, xc.device)
+        r = ratios.detach().to(device=xc.device, dtype=torch.float32).reshape(-1).contiguous()
+        n_cb, n_cand = len(cbs), r.numel()
+        nrow = rows if per_row else 1
+        alpha = torch.empty((n_cb, nrow), dtype=torch.float32, device=xc.device)
+        mse = torch.empty(n_cb, dtype=torch.float32, device=xc.device)
+        idx = torch.empty((n_cb, nrow), dtype=torch.int32, device=xc.device) if want_index else None
+        nws = lib.antq_calibrate_workspace_bytes(rows, cols, int(bool(per_row)), n_cand, n_cb)
+        ws = torch.empty(max(nws, 8), dtype=torch.uint8, device=xc.device)
+        ptrs = (ctypes.c_void_p * n_cb)(*[c.ptr for c in cbs])
+        infos = (ctypes.POINTER(_lib.CodebookInfo) * n_cb)(*[ctypes.pointer(c.info) for c in cbs])
+        fl = (ctypes.c_int * n_cb)(*[(_lib.FLAG_OVP if ovp else 0)] * n_cb)
+        check(lib.antq_calibrate(_ptr(xc), rows, cols, _dtype_code(xc), int(bool(per_row)), _ptr(base), _ptr(r), n_cand,
+                                 ptrs, infos, fl, n_cb, _ptr(alpha), _ptr(mse), _ptr(idx), _ptr(ws), nws, _stream()),
+              "antq_calibrate")
+    return (alpha, mse, idx) if want_index else (alpha, mse)
 
 
 class HostPipeline:

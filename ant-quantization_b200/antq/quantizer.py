@@ -48,29 +48,14 @@ class _FakeQuantSTE(torch.autograd.Function):
     def backward(ctx, g):
         x, out, alpha = ctx.saved_tensors
         q = ctx.quantizer
-        grad_x = None
-        if ctx.needs_input_grad[0]:
-            # mathematically g; the reference's autograd produces fl(fl(g * s) / s) (mul then div), kept bit for bit
-            gmax0 = q._grid_max()
-            if q.is_perchannel:
-                s0 = alpha.reshape(x.shape[0], 1) / gmax0
-                grad_x = ((g.reshape(x.shape[0], -1) * s0) / s0).view(g.shape)
-            else:
-                s0 = alpha / gmax0
-                grad_x = (g * s0) / s0
-        grad_alpha = None
-        if ctx.needs_input_grad[1]:
-            gmax = q._grid_max()
-            if q.is_perchannel:
-                rows = x.shape[0]
-                s = (alpha.reshape(rows, 1).float() / gmax)
-                qd = (out.reshape(rows, -1).float() - x.reshape(rows, -1).float()) / s      # q - d
-                grad_alpha = ((g.reshape(rows, -1).float() * qd).sum(1) / gmax).reshape(ctx.alpha_shape)
-            else:
-                s = alpha.float() / gmax
-                qd = (out.float() - x.float()) / s
-                grad_alpha = ((g.float() * qd).sum() / gmax).reshape(ctx.alpha_shape)
-            grad_alpha = grad_alpha.to(alpha.dtype)
+        need_x, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_x or need_a):
+            return None, None, None
+        # one fused pass (antq_fakequant_backward): grad_x = fl(fl(g * s) / s), exactly what the reference's autograd
+        # produces (mul then div); grad_alpha = sum_row g * (q - d) / max(grid), reduced in a fixed order
+        gx, ga = ops.fakequant_backward(g, x, out, alpha, q._grid_max_host(), q.is_perchannel, need_x, need_a)
+        grad_x = gx.view(g.shape) if need_x else None
+        grad_alpha = ga.reshape(ctx.alpha_shape).to(alpha.dtype) if need_a else None
         return grad_x, grad_alpha, None
 
 
@@ -140,7 +125,7 @@ class Quantizer(nn.Module):
         self.is_enable = False
 
     def update_signed(self, tensor):
-        if tensor.min() < 0:
+        if not self.is_signed and tensor.min() < 0:        # (already signed: nothing to learn, no host round trip)
             self.is_signed = True
 
     # ---------------------------------------------------------------- codebooks
@@ -188,6 +173,10 @@ class Quantizer(nn.Module):
 
     def _grid_max(self):
         return torch.max(self.quant_grid)
+
+    def _grid_max_host(self):
+        """max(quant_grid) as a Python float without a device round trip: the prepared codebook's header has it."""
+        return float(self._codebook(self.quant_grid.device).info.gmax) if self.quant_grid.is_cuda else float(self.quant_grid.max())
 
     def _codebook(self, device):
         """Prepared device codebook, rebuilt only when the grid buffers change
@@ -250,62 +239,96 @@ class Quantizer(nn.Module):
             return [i * 0.01 for i in range(lb, ub)]
         return [i * 0.01 for i in range(lb, ub, 2)]
 
-    def search_mse(self, tensor):
-        """One fused sweep instead of the reference's Python loop: every candidate
-        alpha = base * (i * 0.01) is scored in a single pass over the tensor."""
+    def _calib_inputs(self, tensor):
         per_row = self.is_perchannel and (not self.is_input)
         x = tensor.detach()
         x = x if x.is_contiguous() else x.contiguous()
         base = self._base_alpha(x, per_row).float()
         ratios = torch.tensor(self._candidates(per_row), dtype=torch.float32, device=x.device)
-        cb = self._codebook(x.device)
-        cols = x.numel() // base.numel()
-        ovp = not self._no_outlier()
-        if ovp and (x.numel() % 2 or (per_row and cols % 2)):
-            err = self._sweep_loop(x, base, ratios, per_row)          # pairs straddle rows / wrap around: rare shapes
-        else:
-            err = ops.mse_sweep(x, base, ratios, cb, per_row, ovp=ovp)                       # [n_cand, rows] sums
-        score = err / cols
-        best, idx = score.min(dim=0)                                   # first minimum, like the strict `<` update
-        first = (score == best.unsqueeze(0)).to(torch.int8).argmax(dim=0)
-        alpha = base * ratios[first]
-        if per_row:
-            alpha = alpha.unsqueeze(1)
-            x_max = base.unsqueeze(1)
-        else:
-            alpha = alpha.reshape(())
-            x_max = base.reshape(())
-        self.alpha.data = alpha.to(self.alpha.dtype)
-        return best.sum().float(), alpha, (alpha / x_max).mean().item()
+        return per_row, x, base, ratios
 
-    def _sweep_loop(self, x, base, ratios, per_row):
-        """Candidate loop through the fused forward (shapes the sweep kernel declines)."""
+    _KIND_CODEBOOKS = {}
+
+    def _cb_of_kind(self, kind, device):
+        """Prepared codebook of a grid family: a pure function of (flavour, kind, bits, sign, outliers, device), so it
+        is built once per process -- the type search then costs no codebook build and no host round trip."""
+        key = (self.flavor, kind, self._bits(), bool(self.is_signed), self._no_outlier(), str(device))
+        cb = Quantizer._KIND_CODEBOOKS.get(key)
+        if cb is None:
+            o = None if self._no_outlier() else self.outlier_value().to(device)
+            cb = ops.prepare_codebook(self._grid_for(kind).to(device), o)
+            Quantizer._KIND_CODEBOOKS[key] = cb
+        return cb
+
+    def _score_grids(self, tensor, cbs):
+        """(alpha[n, rows], score[n]) for a list of prepared codebooks: ONE fused launch (antq_calibrate) that reads
+        the tensor once and scores every (grid, alpha candidate) pair; device tensors, no host synchronisation."""
+        per_row, x, base, ratios = self._calib_inputs(tensor)
+        ovp = not self._no_outlier()
+        cols = x.numel() // base.numel()
+        if ovp and (x.numel() % 2 or (per_row and cols % 2)):
+            # pairs straddle rows / wrap around: rare shapes, candidate loop through the fused forward
+            alphas, scores = [], []
+            for cb in cbs:
+                err = self._sweep_loop(x, base, ratios, per_row, cb) / cols
+                best, _ = err.min(dim=0)
+                first = (err == best.unsqueeze(0)).to(torch.int8).argmax(dim=0)
+                alphas.append(base * ratios[first]); scores.append(best.sum().float())
+            return torch.stack(alphas), torch.stack(scores), per_row, base
+        alpha, score = ops.calibrate(x, base, ratios, cbs, per_row, ovp=ovp)
+        return alpha, score, per_row, base
+
+    def _shape_alpha(self, a, per_row):
+        return a.unsqueeze(1) if per_row else a.reshape(())
+
+    def search_mse(self, tensor):
+        """One fused sweep instead of the reference's Python loop: every candidate
+        alpha = base * (i * 0.01) is scored in a single pass over the tensor (A/...:287-326, O/...:190-233)."""
+        alpha, score, per_row, base = self._score_grids(tensor, [self._codebook(tensor.device)])
+        a = self._shape_alpha(alpha[0], per_row)
+        self.alpha.data = a.to(self.alpha.dtype)
+        return score[0], a, (alpha[0] / base).mean()
+
+    def _sweep_loop(self, x, base, ratios, per_row, cb=None):
+        """Candidate loop through the fused forward (shapes the fused calibration declines)."""
+        cb = cb or self._codebook(x.device)
         errs = []
         for r in ratios:
             a = (base * r)
-            q = self._launch(x, a.unsqueeze(1) if per_row else a.reshape(()))
+            q = ops.fakequant(x, a, cb, per_row, not self._no_outlier())
             e = (q.double() - x.double()) ** 2
             errs.append(e.reshape(base.numel(), -1).sum(1))
         return torch.stack(errs)
 
-    def search_adaptive_numeric_type(self, data):
-        """One type per tensor: the candidate whose best summed MSE is smallest
+    def _type_candidates(self):
+        """(token, grid kind the PROBE scores, grid kind the winner gets) in the reference's order
         (A/...:328-415; OliVe: int and flint only, O/...:236-256)."""
-        names, scores = [], []
         mode = self.mode
         order = ["int", "flint"] if self.flavor == "olive" else \
             ["int", "flint", "pot", "float", "float1", "float2", "float3", "float4", "apot"]
+        out = []
         for tok in order:
             if ("-" + tok) not in mode:
                 continue
             # reference quirk kept: the -float2/3/4 probes all score float_value(1) (A/...:379,388,397)
-            kind = "float1" if tok in ("float2", "float3", "float4") else tok
-            self.mode = tok
-            self.quant_grid.data = self._grid_for(kind)
-            s, _, _ = self.search_mse(data)
-            names.append(tok)
-            scores.append(s.item())
-        self.mode = names[int(np.argsort(np.array(scores))[0])]
+            out.append((tok, "float1" if tok in ("float2", "float3", "float4") else tok, tok))
+        return out
+
+    def search_adaptive_numeric_type(self, data):
+        """One type per tensor: the candidate whose best summed MSE is smallest.  All candidate types (and the winner's
+        final grid) are scored by ONE launch; the only host read is the handful of per-type scores."""
+        cands = self._type_candidates()
+        kinds = []
+        for _, probe, final in cands:
+            for k in (probe, final):
+                if k not in kinds:
+                    kinds.append(k)
+        alpha, score, per_row, _ = self._score_grids(data, [self._cb_of_kind(k, data.device) for k in kinds])
+        host = score.cpu().numpy()                                      # the one synchronisation of the type search
+        probe_scores = np.array([host[kinds.index(p)] for _, p, _ in cands])
+        win = cands[int(np.argsort(probe_scores)[0])]
+        self.mode = win[0]
+        self._calibrated = (self._grid_for(win[2]), self._shape_alpha(alpha[kinds.index(win[2])], per_row))
 
     def outlier_set(self, data):
         """OLAccel-style baseline (mode == 'outlier', A/...:417-436): the int-4 window ends at the `percent`
@@ -377,6 +400,7 @@ class Quantizer(nn.Module):
             if self.flavor == "ant" and self.mode == 'outlier':
                 return self.outlier_set(data)
 
+            self._calibrated = None
             if self.bit > 6:
                 self.mode = 'int'
             elif "ant-" in self.mode:
@@ -386,9 +410,15 @@ class Quantizer(nn.Module):
                 ("int", "flint", "pot", "apot", "float", "float1", "float2", "float3", "float4")
             if self.mode not in valid:
                 raise RuntimeError("Unsupported mode: " + self.mode)
-            self.quant_grid.data = self._grid_for(self.mode)
-
-            _, alpha, _ = self.search_mse(data)
+            if self._calibrated is not None:
+                # the type search already scored the winner's own grid: the final search_mse of the reference
+                # (A/...:513) would repeat exactly that computation
+                grid, alpha = self._calibrated
+                self.quant_grid.data = grid
+                self._calibrated = None
+            else:
+                self.quant_grid.data = self._grid_for(self.mode)
+                _, alpha, _ = self.search_mse(data)
             self.alpha.data = alpha.to(self.alpha.dtype)
 
             quant_data = self._forward(data)

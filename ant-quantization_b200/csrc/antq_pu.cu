@@ -60,9 +60,11 @@ __device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
 
 struct PuRow {
     float s, kx, xl;
+    uint32_t xl2;                     // 16-bit types: xl rounded toward zero, in both halves
     bool ok;
 };
 
+template <typename T>
 __device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const PuK &K, bool fast_rcp) {
     PuRow r;
     const float inf = __int_as_float(0x7f800000);
@@ -73,6 +75,11 @@ __device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const Pu
     r.kx = __fmul_rn(rs, K.inv_c);
     r.ok = r.s > 0.0f && r.s < inf && r.kx > 0.0f && r.kx < inf;
     r.xl = __fmul_rn(__fmul_rn(p.lim, r.s), 0.9990234375f);           // conservative exact window in x-space
+    r.xl2 = 0;
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t b = AntqType<T>::bits(AntqType<T>::from_f32_rz(r.xl));
+        r.xl2 = b | (b << 16);
+    }
     return r;
 }
 
@@ -83,7 +90,7 @@ __device__ __forceinline__ float pu_quant(float xf, const PuRow &r, const PuK &K
     float M, dl;
     if (UNIFORM) {
         M = 12582912.0f;                                              // 1.5 * 2^23: step 1 everywhere
-        dl = fmaxf(__fmul_rn(fabsf(t), 1.9073486328125e-06f), 9.5367431640625e-07f);   // max(|t| 2^-19, 2^-20)
+        dl = __fmul_rn(fabsf(t), 1.9073486328125e-06f);               // |t| 2^-19 (2^-20 at the first midpoint, t = 0.5)
     } else {
         const float2 md = tab[__float_as_uint(t) >> 23];              // sign + exponent index a 512-entry table
         M = md.x; dl = md.y;
@@ -97,18 +104,37 @@ __device__ __forceinline__ float pu_quant(float xf, const PuRow &r, const PuK &K
     return __fmul_rn(q, r.s);
 }
 
+// Exact thresholds and levels of the codebook, staged in shared memory for the redo path (the rank search is 3-8
+// dependent loads: from global memory that costs several microseconds per flagged element).
+struct PuExact {
+    const float *thr, *lev;           // shared memory, n_levels - 1 and n_levels entries
+    int nlev;
+    float win;                        // |d| <= win: the threshold search equals the scan (else the literal scan)
+};
+
 // The reference arithmetic for ONE element, literally (exact thresholds inside the proven window, else the scan).
-template <typename T> __device__ __noinline__ T pu_exact_elem(const AntqCodebook *__restrict__ cb, float xf, float s) {
+template <typename T>
+__device__ __noinline__ T pu_exact_elem(const AntqCodebook *__restrict__ cb, const PuExact X, float xf, float s) {
     const float d = __fdiv_rn(xf, s);
     float q;
-    if ((cb->flags & ANTQ_CB_WELLSEP) && fabsf(d) <= cb->lim_idx) {
-        q = cb->level[antq_rank(cb->thr, cb->n_levels - 1, d)];
+    if (fabsf(d) <= X.win) {
+        q = X.lev[antq_rank(X.thr, X.nlev - 1, d)];
     } else {
         int code;
         q = antq_scan_literal(cb->grid, cb->n_entries, d, code);
     }
     return AntqType<T>::from_f32_rn(antq_ste_rescale(q, d, s));
 }
+
+template <typename T> struct PuPack { typedef float2 v2; };
+template <> struct PuPack<__half> {
+    typedef __half2 v2;
+    __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
+};
+template <> struct PuPack<__nv_bfloat16> {
+    typedef __nv_bfloat162 v2;
+    __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
+};
 
 template <typename T> struct PuIO;
 template <> struct PuIO<float> {
@@ -161,7 +187,16 @@ __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const P
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
         o[e] = pu_quant<UNIFORM>(f[e], r, K, tab, fl);
-        fl |= !(fabsf(f[e]) <= r.xl);                                 // outside the exact window, NaN, Inf
+        if (sizeof(T) == 4) fl |= !(fabsf(f[e]) <= r.xl);             // outside the exact window, NaN, Inf
+    }
+    if (sizeof(T) == 2) {
+        // 16-bit types: one packed NaN-propagating max of |x| per vector against the window
+        if constexpr (sizeof(T) == 2) {
+            typedef typename PuPack<T>::v2 v2;
+            const v2 a = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.x)), __habs2(PuPack<T>::from_u32(raw.y)));
+            const v2 b = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.z)), __habs2(PuPack<T>::from_u32(raw.w)));
+            fl |= __hle2_mask(__hmax2_nan(a, b), PuPack<T>::from_u32(r.xl2)) != 0xffffffffu;
+        }
     }
     flag = fl;
     return PuIO<T>::pack(o);
@@ -169,8 +204,8 @@ __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const P
 
 // Redo of the flagged elements of one vector (the vector itself has already been stored by this thread).
 template <typename T, bool UNIFORM>
-__device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, const uint4 raw, const PuRow r, const PuK K,
-                                         const float2 *tab, T *og) {
+__device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, const PuExact X, const uint4 raw, const PuRow r,
+                                         const PuK K, const float2 *tab, T *og) {
     constexpr int VEC = PuIO<T>::VEC;
     float f[VEC];
     PuIO<T>::unpack(raw, f);
@@ -181,7 +216,7 @@ __device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, co
             (void)pu_quant<UNIFORM>(f[e], r, K, tab, fl);
             fl |= !(fabsf(f[e]) <= r.xl);
         }
-        if (fl) og[e] = pu_exact_elem<T>(cb, f[e], r.s);
+        if (fl) og[e] = pu_exact_elem<T>(cb, X, f[e], r.s);
     }
 }
 
@@ -198,7 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     constexpr int VEC = A::kVec;
     extern __shared__ __align__(128) unsigned char pu_smem[];
     float2 *tab = reinterpret_cast<float2 *>(pu_smem + (size_t)kNS * kChunkMax);          // 512 entries
-    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 512);
+    float *x_thr = reinterpret_cast<float *>(tab + 512);                                  // exact thresholds / levels (redo path)
+    float *x_lev = x_thr + ANTQ_MAX_GRID;
+    uint64_t *full = reinterpret_cast<uint64_t *>(x_lev + ANTQ_MAX_GRID);
     unsigned *next_k = reinterpret_cast<unsigned *>(full + kNS);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -257,6 +294,10 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     if (!UNIFORM) {
         for (int i = threadIdx.x; i < 512; i += kThreads) tab[i] = cb->pu_tab[i & 255];
     }
+    PuExact X;
+    X.thr = x_thr; X.lev = x_lev; X.nlev = cb->n_levels;
+    X.win = (cb->flags & ANTQ_CB_WELLSEP) ? cb->lim_idx : -1.0f;
+    for (int i = threadIdx.x; i < X.nlev; i += kThreads) { x_thr[i] = cb->thr[i]; x_lev[i] = cb->level[i]; }
     const PuK K = pu_load_k(cb);
     __syncthreads();
 
@@ -270,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             cur = geo_of(kn);
             request(cur, warp + (slot ^ 1) * kNC);
         }
-        const PuRow r = pu_row(g.alpha, p, K, false);
+        const PuRow r = pu_row<T>(g.alpha, p, K, false);
         const int nvec = g.nvec;
         const uint4 *sv = reinterpret_cast<const uint4 *>(pu_smem + (size_t)stage * kChunkMax);
         T *og = reinterpret_cast<T *>(p.out) + g.base;
@@ -309,14 +350,14 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             for (int j = 0; j * 32 + lane < nvec; j++) {
                 if ((redo >> j) & 1u) {
                     const int v = j * 32 + lane;
-                    pu_redo_vec<T, UNIFORM>(cb, sv[v], r, K, tab, og + (long long)v * VEC);
+                    pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
                 }
             }
         }
         if (g.tail > 0 && lane == 0) {                                 // ragged tail of a per-tensor view
             const T *xg = reinterpret_cast<const T *>(p.x) + g.base + (long long)nvec * VEC;
             for (int e = 0; e < g.tail; e++)
-                og[(long long)nvec * VEC + e] = pu_exact_elem<T>(cb, A::to_f32(xg[e]), r.s);
+                og[(long long)nvec * VEC + e] = pu_exact_elem<T>(cb, X, A::to_f32(xg[e]), r.s);
         }
         __syncwarp();
         k = kn;
@@ -333,11 +374,16 @@ template <typename T, bool UNIFORM>
 __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const PuParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
-    __shared__ float2 tab[512];
+    __shared__ float2 tab[UNIFORM ? 1 : 512];
+    __shared__ float x_thr[ANTQ_MAX_GRID], x_lev[ANTQ_MAX_GRID];
     if (!UNIFORM) {
         for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
-        __syncthreads();
     }
+    PuExact X;
+    X.thr = x_thr; X.lev = x_lev; X.nlev = p.cb->n_levels;
+    X.win = (p.cb->flags & ANTQ_CB_WELLSEP) ? p.cb->lim_idx : -1.0f;
+    for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
+    __syncthreads();
     const PuK K = pu_load_k(p.cb);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
@@ -346,18 +392,18 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
         const uint4 raw = antq_ldg_stream(xin + v);
         unsigned row = 0;
         if (p.alpha_per_row) row = p.cols_shift >= 0 ? v >> p.cols_shift : v / p.cols_vec;
-        const PuRow r = pu_row(__ldg(p.alpha + row), p, K, true);
+        const PuRow r = pu_row<T>(__ldg(p.alpha + row), p, K, true);
         bool flag = true;
         uint4 q = raw;
         if (r.ok) q = pu_vec<T, UNIFORM>(raw, r, K, tab, flag);
         antq_stg_stream(xout + v, q);
-        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
     }
 }
 
 template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_pu_stream_kernel<T, UNIFORM>;
-    const int smem = kNS * kChunkMax + 512 * 8 + kNS * 8 + 16;
+    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16;
     static unsigned long long configured = 0ull;                     // one bit per device ordinal
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -15,6 +15,9 @@
  *   antq_absmax             the abs-max alpha init           A/antquant/quant_modules.py:473-477
  *   antq_mse_sweep          search_mse's candidate loop      A/antquant/quant_modules.py:287-326,
  *                                                             O/antquant/quant_modules.py:190-233
+ *   antq_calibrate          search_mse + search_adaptive_numeric_type, fused   A/antquant/quant_modules.py:287-415
+ *   antq_fakequant_backward autograd of _forward (QAT)                 A/antquant/quant_modules.py:535-551
+ *   antq_encode_p4 / antq_decode_p4   the never-written `tensor_idx`   A/quant/quant_kernel.cu:18,49,61
  *   antq_host_*             the same forward for HOST buffers (copies inside)
  *
  * Conventions
@@ -126,6 +129,47 @@ int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype
 int antq_mse_sweep(const void *x, const float *base_alpha, int alpha_per_row, const float *ratios, int n_cand,
                    double *err, int64_t rows, int64_t cols, int dtype, const void *codebook, int flags,
                    void *stream);
+
+/* ---- packed 4-bit code storage ("P4"), the second output the reference kernel allocates and never writes
+ * (`tensor_idx`, A/quant/quant_kernel.cu:18,49,61) ----
+ * Byte j of a row = code of element 2j (low nibble) | code of element 2j + 1 (high nibble); a code is the index into
+ * `quant_grid` of the level the scan selects.  OliVe with outliers (normal grid <= 15 entries): nibble 15 marks the
+ * victim of an outlier-victim pair and the other nibble then indexes `outliers` (O/antquant/quant_modules.py:311-320).
+ * cols must be even, the grid at most 16 entries (15 + 15 with outliers).
+ * n_inexact (device, optional) receives the number of elements whose fake-quant value antq_decode_p4 would NOT
+ * reproduce bit for bit (STE rounding of values clipped beyond twice the largest level, NaN, Inf): zero means
+ * decode(encode(x)) == antq_fakequant(x) everywhere. */
+int antq_encode_p4(const void *x, uint8_t *codes, const float *alpha, int alpha_per_row, int64_t rows, int64_t cols,
+                   int dtype, const void *codebook, const antq_codebook_info *info, int flags, unsigned int *n_inexact,
+                   void *stream);
+int antq_decode_p4(const uint8_t *codes, void *out, const float *alpha, int alpha_per_row, int64_t rows, int64_t cols,
+                   int dtype, const void *codebook, const antq_codebook_info *info, int flags, void *stream);
+
+/* ---- QAT backward of Quantizer._forward under autograd (A/antquant/quant_modules.py:535-551; driver
+ * A/ImageNet/main.py:190-198): one pass over (grad_out, x, out).
+ *   grad_x[i]     = fl(fl(g * s) / s)                      (what autograd's mul-then-div produces; NULL to skip)
+ *   grad_alpha[r] = sum_row g * (out - x) / s / max(grid)  (per row, or one value; NULL to skip)
+ * Deterministic (fixed-order fp64 reduction through `workspace`, antq_backward_workspace_bytes bytes). */
+size_t antq_backward_workspace_bytes(int64_t rows, int64_t cols, int alpha_per_row);
+int antq_fakequant_backward(const void *grad_out, const void *x, const void *out, const float *alpha, int alpha_per_row,
+                            int64_t rows, int64_t cols, int dtype, float gmax, void *grad_x, float *grad_alpha,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- fused calibration: search_mse + search_adaptive_numeric_type in one read of the tensor
+ * (A/antquant/quant_modules.py:287-326,328-415; O/antquant/quant_modules.py:190-256) ----
+ * Every candidate alpha = base_alpha[row] * ratios[c] of every codebook k is scored (mean squared error of the
+ * fake-quant forward per row).  Outputs, all on the device, no host synchronisation:
+ *   alpha_out[k][row]   the FIRST strictly-best candidate's alpha (base itself if no candidate beats 1e10, as the
+ *                       reference's `score < best_score` update leaves it)
+ *   mse_out[k]          sum over rows of the best mean squared error: the reference's type-selection score
+ *   best_index_out      optional [k][row] candidate index (-1: none)
+ * codebooks / infos / flags_per_codebook are HOST arrays of n_cb (<= 8) entries (device codebook pointers, host
+ * headers, ANTQ_FLAG_OVP per codebook).  n_cand <= 256.  Deterministic: fixed-order fp64 reductions in `workspace`. */
+size_t antq_calibrate_workspace_bytes(int64_t rows, int64_t cols, int alpha_per_row, int n_cand, int n_cb);
+int antq_calibrate(const void *x, int64_t rows, int64_t cols, int dtype, int alpha_per_row, const float *base_alpha,
+                   const float *ratios, int n_cand, const void *const *codebooks, const antq_codebook_info *const *infos,
+                   const int *flags_per_codebook, int n_cb, float *alpha_out, float *mse_out, int *best_index_out,
+                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer path (what a CPU caller of the reference would use) ---- */
 typedef struct antq_host_ctx antq_host_ctx;

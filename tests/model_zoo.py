@@ -102,6 +102,7 @@ def vit():
     torch.manual_seed(4)
     m = torchvision.models.VisionTransformer(image_size=32, patch_size=8, num_layers=2, num_heads=4, hidden_dim=64,
                                              mlp_dim=128, num_classes=10).eval()
+    torch.nn.init.normal_(m.heads.head.weight, std=0.05)      # torchvision zero-inits the head: alpha = 0, NaN logits
     x = torch.randn(2, 3, 32, 32)
     return m, (x,), {}, _args("ant-int-pot-flint", w_low=80, a_low=40)
 

@@ -82,6 +82,35 @@ for n, e in ref.items():
         if crc(o) != e["crc"]:
             a_bad.append(n)
 yr = torch.from_numpy(fix["y"]).to(dev)
+# ---- end to end, exactly: the same GPU model with every fused launch replaced by the CPU oracle (literal scan) ----
+sys.path.insert(0, %(oracle)r)
+import antq_oracle as orc
+from antq.quantizer import Quantizer
+def oracle_launch(self, x, alpha):
+    xc = x.detach().contiguous()
+    xn = xc.cpu().numpy()
+    a = alpha.detach().float().cpu().numpy().reshape(-1)
+    g = self.quant_grid.detach().float().cpu().numpy()
+    per_row = bool(self.is_perchannel)
+    a = a if per_row else np.float32(a[0])
+    if self.flavor == "olive":
+        o = self.outliers.detach().float().cpu().numpy()
+        y = orc.olive_forward(xn, a, g, o, per_row=per_row, no_outlier=self._no_outlier())
+    else:
+        y = orc.ant_forward(xn, a, g, per_row=per_row)
+    return torch.from_numpy(np.ascontiguousarray(y)).to(x.device).view(x.shape)
+real_launch = Quantizer._launch
+Quantizer._launch = oracle_launch
+import antq.layers as L
+L.CACHE_WEIGHTS = False
+with torch.no_grad():
+    y_orc = logits(q(*xs_d, **kw))
+Quantizer._launch = real_launch
+with torch.no_grad():
+    y_again = logits(q(*xs_d, **kw))
+L.CACHE_WEIGHTS = True
+RESULT["e2e_bit_exact"] = bool(torch.equal(y_orc, y_again) and torch.equal(y, y_again))
+RESULT["e2e_maxdiff"] = float((y_orc - y_again).abs().max())
 RESULT.update(w_n=w_n, w_bad=w_bad, a_n=a_n, a_bad=a_bad,
               pinned_rel=float((y - yr).norm() / yr.norm()),
               quant_effect=float((torch.from_numpy(fix["y_fp32"]).to(dev) - yr).norm() / yr.norm()))
@@ -124,23 +153,27 @@ def test_zoo_model_matches_reference(name):
         pytest.skip("fixture zoo_%s.npz not generated" % name)
     import model_zoo
     tree = model_zoo.ZOO[name][0]
-    res, out = run(tree, ZOO_BODY % dict(tests=os.path.join(ROOT, "tests"), golden=GOLDEN, name=name), timeout=1500)
+    res, out = run(tree, ZOO_BODY % dict(tests=os.path.join(ROOT, "tests"), oracle=os.path.join(ROOT, "oracle"), golden=GOLDEN, name=name), timeout=1500)
     print(json.dumps(res))
     assert res["checksum_rel"] < 1e-12, "random init differs from the fixture's: %r" % res["checksum_rel"]
     assert res["same_names"]
     # pinned: every quantizer output bit-identical to the reference's
     assert res["w_n"] > 0 and res["w_bad"] == [], res
     assert res["a_n"] > 0 and res["a_bad"] == [], res
-    # logits: GPU GEMM / conv accumulation order differs from the CPU's, and a 1-ulp change in a pre-quantizer
-    # activation can move it across a 4-bit threshold; the bound is 2 % of the logits' norm and at most a fifth of
-    # the quantization effect itself (|y_fp32 - y_quant|)
-    assert res["pinned_rel"] < 2e-2 and res["pinned_rel"] < 0.2 * max(res["quant_effect"], 1e-3), res
+    # end to end on one device: the model run with the fused kernels and the SAME model with every launch replaced by
+    # the CPU oracle (identical cuDNN / cuBLAS calls around them) must give bit-identical logits
+    assert res["e2e_bit_exact"], res
+    # against the CPU reference's logits only a loose bound is meaningful: cuDNN / cuBLAS accumulate in another order
+    # than the CPU kernels, a 1-ulp change in a pre-quantizer activation can cross a 4-bit threshold, and that
+    # compounds over 12-54 quantized layers (every quantizer in isolation is bit-exact, asserted above).  Bound: less
+    # than half of the quantization effect itself, |y_fp32 - y_quant| / |y_quant|.
+    assert res["pinned_rel"] < 0.5 * max(res["quant_effect"], 1e-3), res
     # calibration from scratch: same sign everywhere, same type on >= 90 % of the quantizers (a type flips only when
     # two candidates' summed MSEs agree to fp32 noise), alpha identical on >= 90 % of the channels
     assert res["sign_ok"] == res["n_q"], res
     assert res["mode_ok"] >= 0.9 * res["n_q"], res
     assert res["alpha_exact_frac"] >= 0.9, res
-    assert res["calib_rel"] < 0.25 * max(res["quant_effect"], 1e-2) + 2e-2, res
+    assert res["calib_rel"] < 0.5 * max(res["quant_effect"], 1e-3), res
 
 
 MODULES_BODY = r'''
