@@ -65,6 +65,7 @@ def _load():
     L.antq_calibrate_workspace_bytes.restype = sz
     L.antq_calibrate.argtypes = [vp, i64, i64, ci, ci, vp, vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ip), ctypes.POINTER(ci),
                                  ci, vp, vp, vp, vp, sz, vp]
+    L.antq_linear_p4.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, vp, ip, ci, vp]
     L.antq_host_create.argtypes = [ctypes.POINTER(vp), ci, sz, ci]
     L.antq_host_destroy.argtypes = [vp]
     L.antq_host_destroy.restype = None
@@ -75,7 +76,7 @@ def _load():
     for name in ("antq_codebook_prepare", "antq_codebook_info_get", "antq_lut_nearest", "antq_fakequant",
                  "antq_fakequant_plan", "antq_absmax", "antq_mse_sweep", "antq_host_create",
                  "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches",
-                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate"):
+                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate", "antq_linear_p4"):
         getattr(L, name).restype = ci
     return L
 

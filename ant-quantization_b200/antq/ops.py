@@ -309,6 +309,26 @@ def calibrate(x, base_alpha, ratios, cbs, per_row, ovp=False, want_index=False):
     return (alpha, mse, idx) if want_index else (alpha, mse)
 
 
+def linear_p4(x, codes, alpha, cb, out_features, bias=None):
+    """y = x . dequant(W)^T + bias on the tensor cores (antq_linear_p4): W is [out_features, in_features] held as packed
+    4-bit codes + one alpha per output channel.  x: [..., in_features] fp16 / bf16 CUDA tensor."""
+    _need_cuda(x, "x")
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, N = x2.shape[0], int(out_features)
+    with _maybe_guard(x.device):
+        a = _alpha_arg(alpha, N, True, x.device)
+        b = None
+        if bias is not None:
+            b = bias if (bias.dtype is x.dtype and bias.is_contiguous()) else bias.detach().to(x.dtype).contiguous()
+        y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        check(lib.antq_linear_p4(_ptr(x2), _ptr(codes), _ptr(a), _ptr(b), _ptr(y), M, N, K, _dtype_code(x2), cb.ptr,
+                                 cb.info_ref, 0, _stream()), "antq_linear_p4")
+    return y.view(*x.shape[:-1], N)
+
+
 class HostPipeline:
     """antq_host_*: fake-quant of HOST buffers (H2D, kernel, D2H pipelined in chunks)."""
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 SUFFIX = os.environ.get("ANTQ_LIB_SUFFIX", "")
 OUT = os.path.join(CSRC, "libantq%s.so" % SUFFIX)
 SOURCES = ["antq_prepare.cu", "antq_stream.cu", "antq_pu.cu", "antq_short.cu", "antq_flat.cu", "antq_codes.cu", "antq_bwd.cu",
-           "antq_calib.cu", "antq_capi.cu"]
+           "antq_calib.cu", "antq_gemm.cu", "antq_capi.cu"]
 HEADERS = ["antq_common.cuh", os.path.join("..", "..", "include", "antq.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -51,8 +51,13 @@ template <typename T, bool OVP> __global__ void __launch_bounds__(kThreads) antq
     const T *x = reinterpret_cast<const T *>(p.x) + i0;
     const int cnt = (int)((p.n - i0) < 8 ? (p.n - i0) : 8);            // n is even, rows are even: cnt is even
     T xv[8];
-    if (cnt == 8 && ((uintptr_t)x % 16 == 0)) *reinterpret_cast<uint4 *>(xv) = antq_ldg_stream(reinterpret_cast<const uint4 *>(x));
-    else for (int e = 0; e < cnt; e++) xv[e] = x[e];
+    if (cnt == 8 && ((uintptr_t)x % 16 == 0)) {
+#pragma unroll
+        for (int k = 0; k < (int)(8 * sizeof(T) / 16); k++)
+            reinterpret_cast<uint4 *>(xv)[k] = antq_ldg_stream(reinterpret_cast<const uint4 *>(x) + k);
+    } else {
+        for (int e = 0; e < cnt; e++) xv[e] = x[e];
+    }
     long long row = p.alpha_per_row ? i0 / p.cols : 0;
     long long col = p.alpha_per_row ? i0 - row * p.cols : 0;
     float s = __fdiv_rn(p.alpha[row], gmax);

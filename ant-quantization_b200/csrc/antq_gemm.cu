@@ -1,0 +1,361 @@
+// antq_gemm.cu -- dequant-fused Linear on the 5th-generation tensor cores:
+//
+//     y[M, N] = x[M, K] . dequant(W)[N, K]^T + bias[N]
+//
+// What it replaces: LinearQuantizer.forward's  F.linear(quant_input(x), quant_weight(W), bias)
+// (A/antquant/quant_modules.py:642-646; torch.addmm in O/antquant/quant_modules.py:379) when the weight is held as
+// packed 4-bit codes (antq_codes.cu: 0.5 byte per element + one fp32 alpha per output channel) instead of a
+// re-fake-quantized fp16 / fp32 tensor.  x is the (already fake-quantized) activation, fp16 or bf16.
+//
+// Arithmetic.  W_q[n, k] = level[code[n, k]] * s_n with s_n = alpha_n / max(grid).  The kernel multiplies the
+// UNSCALED levels (rounded once to the 16-bit operand type; every ANT 4-bit flint / pot / float level and every OliVe
+// level is exact in fp16) on the tensor cores, accumulates in fp32 in tensor memory, and applies s_n and the bias in
+// the epilogue:  y = fl16(acc * s_n + bias).  Against F.linear on the fake-quantized operands this differs by fp32
+// accumulation order and one 16-bit rounding per weight (2^-12 relative, uncorrelated): tolerance in the test.
+//
+// Structure (one CTA per SM, persistent over 128 x 128 output tiles, BK = 64, kStages-deep shared-memory ring):
+//   warp 4      TMA producer: x tiles [128 x 64] by cp.async.bulk.tensor.2d (128-byte swizzle) -> full[stage]
+//   warps 6-9   weight decoders: thread = one output channel of the tile; 32 bytes of codes -> 64 operand values through
+//               a 16-entry byte LUT held in registers (PRMT), written in the same K-major 128-byte-swizzled layout
+//               -> fence.proxy.async -> full[stage]
+//   warp 5      MMA issuer: one lane issues 4 x tcgen05.mma (M128 N128 K16, kind::f16) per stage into one of two
+//               128-column accumulators in tensor memory; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, bias, 16-bit stores; overlaps the next
+//               tile's main loop through the second accumulator
+// SASS evidence: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld): profiles/r02_gemm_sass.txt.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "antq_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 5;
+constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;            // bytes (16-bit operands)
+constexpr int kEpiWarps = 4, kTmaWarp = 4, kMmaWarp = 5, kDecWarp0 = 6, kDecWarps = 4;
+constexpr int kThreads = (kDecWarp0 + kDecWarps) * 32;                 // 320
+constexpr int kTmemCols = 256;                                         // two fp32 accumulators of 128 columns
+
+struct GemmParams {
+    const unsigned char *codes;       // [N, K / 2]
+    const float *alpha;               // [N]
+    const void *bias;                 // [N] (operand type) or NULL
+    void *y;                          // [M, N]
+    const AntqCodebook *cb;
+    int M, N, K;
+    int m_tiles, n_tiles;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(antq_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(antq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ANTQG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ANTQG_DONE;\n"
+        "bra ANTQG_WAIT;\n"
+        "ANTQG_DONE:\n"
+        "}\n" ::"r"(antq_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(antq_smem_u32(dst)), "l"(map), "r"(antq_smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 |
+// SBO << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <typename T> struct Op16;
+template <> struct Op16<__half> {
+    static constexpr uint32_t kFormat = 0;                      // cute::UMMA::F16F32Format::F16
+    __device__ static __forceinline__ uint32_t bits(float v) { return __half_as_ushort(__float2half_rn(v)); }
+    __device__ static __forceinline__ float to_f32(__half v) { return __half2float(v); }
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        const __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+};
+template <> struct Op16<__nv_bfloat16> {
+    static constexpr uint32_t kFormat = 1;                      // BF16
+    __device__ static __forceinline__ uint32_t bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+    __device__ static __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ uint32_t pack(float a, float b) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+};
+
+// Four 4-bit codes (the low 16 bits of `c`) -> four 16-bit operand values, through the 16-entry byte LUTs
+// lo[0..3] / hi[0..3] (entry e's low / high byte sits in byte e % 4 of register e / 4).  PRMT is an 8-entry byte LUT
+// with four lookups per instruction: one PRMT per half of the table, a third picks the half by bit 3 of each code.
+__device__ __forceinline__ void lut4(uint32_t c, const uint32_t (&lo)[4], const uint32_t (&hi)[4], uint32_t &out01, uint32_t &out23) {
+    const uint32_t sel = c & 0x7777u;
+    const uint32_t pick = 0x3210u | ((c & 0x8888u) >> 1);
+    const uint32_t l = __byte_perm(__byte_perm(lo[0], lo[1], sel), __byte_perm(lo[2], lo[3], sel), pick);
+    const uint32_t h = __byte_perm(__byte_perm(hi[0], hi[1], sel), __byte_perm(hi[2], hi[3], sel), pick);
+    out01 = __byte_perm(l, h, 0x5140u);
+    out23 = __byte_perm(l, h, 0x7362u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char gsm_raw[];
+    // the 128-byte swizzle pattern is a function of the shared-memory ADDRESS: tiles must start 1024-byte aligned
+    unsigned char *gsm = gsm_raw + ((1024u - (antq_smem_u32(gsm_raw) & 1023u)) & 1023u);
+    unsigned char *smem_a = gsm;                                           // kStages x 16 KiB, 1024-byte aligned
+    unsigned char *smem_b = gsm + kStages * kStageA;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + kStages * kStageB);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;                                 // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                                  // [2]
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *s_scale = reinterpret_cast<float *>(tmem_base_slot + 4);        // [2][BN] alpha / max(grid) of the tile's channels
+    float *s_bias = s_scale + 2 * BN;                                      // [2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.K / BK;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(full + s, 1 + kDecWarps * 32); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, kEpiWarps * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kTmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(antq_smem_u32(tmem_base_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == kTmaWarp) {
+        // ------------------------------ TMA producer (x tiles) ------------------------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+            int stage = 0;
+            unsigned phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m_blk = t % p.m_tiles;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    mbar_expect_tx(full + stage, kStageA);
+                    tma_load_2d(smem_a + stage * kStageA, &tmap_x, full + stage, kb * BK, m_blk * BM);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A / B format << 7 / << 10, K-major both, N >> 3 << 17, M >> 4 << 24
+            const uint32_t idesc = (1u << 4) | (Op16<T>::kFormat << 7) | (Op16<T>::kFormat << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            unsigned phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
+                const int acc = it & 1;
+                mbar_wait(tmem_empty + acc, ((it >> 1) & 1) ^ 1u);                 // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(full + stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t adesc = umma_desc(antq_smem_u32(smem_a + stage * kStageA));
+                    const uint64_t bdesc = umma_desc(antq_smem_u32(smem_b + stage * kStageB));
+#pragma unroll
+                    for (int j = 0; j < BK / 16; j++)                               // K = 16 per instruction = 32 bytes = 2 x 16 B
+                        umma_f16(d_tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0);
+                    umma_commit(empty + stage);                                     // frees the stage when these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tmem_full + acc);                                       // accumulator complete
+            }
+        }
+    } else if (warp >= kDecWarp0) {
+        // ------------------------------ weight decoders ------------------------------
+        const int n_local = threadIdx.x - kDecWarp0 * 32;                           // 0..127: the tile's output channel
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const uint32_t b = e < p.cb->n_entries ? Op16<T>::bits(p.cb->grid[e]) : 0u;
+            lo[e >> 2] |= (b & 0xffu) << (8 * (e & 3));
+            hi[e >> 2] |= (b >> 8) << (8 * (e & 3));
+        }
+        const int row_off = (n_local >> 3) * 1024 + (n_local & 7) * 128;
+        const int sw = n_local & 7;
+        int stage = 0;
+        unsigned phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_blk = t / p.m_tiles;
+            const unsigned char *crow = p.codes + (size_t)(n_blk * BN + n_local) * (size_t)(p.K / 2);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const uint4 c0 = __ldg(reinterpret_cast<const uint4 *>(crow + kb * (BK / 2)));
+                const uint4 c1 = __ldg(reinterpret_cast<const uint4 *>(crow + kb * (BK / 2)) + 1);
+                mbar_wait(empty + stage, phase ^ 1u);
+                unsigned char *dst = smem_b + stage * kStageB + row_off;
+                const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {                                       // one 32-bit word = 8 codes = one 16-byte chunk
+                    uint4 v;
+                    lut4(w[j], lo, hi, v.x, v.y);
+                    lut4(w[j] >> 16, lo, hi, v.z, v.w);
+                    *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> tensor-core reads
+                mbar_arrive(full + stage);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------ epilogue (warps 0-3 = tensor-memory lanes 32 w .. 32 w + 31) ------------------------------
+        const float gmax = p.cb->gmax;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+            float *sc = s_scale + acc * BN, *bs = s_bias + acc * BN;
+            {
+                const int n = n_blk * BN + threadIdx.x;                            // 128 epilogue threads: one channel each
+                sc[threadIdx.x] = __fdiv_rn(p.alpha[n], gmax);
+                bs[threadIdx.x] = p.bias ? Op16<T>::to_f32(reinterpret_cast<const T *>(p.bias)[n]) : 0.0f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                          // the epilogue warps only
+            mbar_wait(tmem_full + acc, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = m_blk * BM + warp * 32 + lane;
+            T *yrow = reinterpret_cast<T *>(p.y) + (size_t)m * p.N + (size_t)n_blk * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c), v);
+                if (m < p.M) {
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8) {
+                        uint4 o;
+                        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            ow[e >> 1] = Op16<T>::pack(__fmaf_rn(__uint_as_float(v[q + e]), sc[c + q + e], bs[c + q + e]),
+                                                       __fmaf_rn(__uint_as_float(v[q + e + 1]), sc[c + q + e + 1], bs[c + q + e + 1]));
+                        *reinterpret_cast<uint4 *>(yrow + c + q) = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty + acc);
+            asm volatile("bar.sync 1, 128;" ::: "memory");                          // sc / bs of this accumulator may be rewritten
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kTmaWarp)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <typename T> int launch(const CUtensorMap &map, const GemmParams &p, int ctas, cudaStream_t st) {
+    const int smem = kStages * (kStageA + kStageB) + (2 * kStages + 4) * 8 + 16 + 4 * BN * 4 + 1024;
+    static unsigned long long configured = 0ull;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 64 || !((configured >> dev) & 1ull)) {
+        e = cudaFuncSetAttribute(antq_linear_p4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev < 64) configured |= 1ull << dev;
+    }
+    antq_linear_p4_kernel<T><<<ctas, kThreads, smem, st>>>(map, p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int antq_linear_p4(const void *x, const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M,
+                              int64_t N, int64_t K, int dtype, const void *codebook, const antq_codebook_info *info, int flags,
+                              void *stream) {
+    if (M < 0 || N < 0 || K < 0 || !info) return ANTQ_EINVAL;
+    if (M == 0 || N == 0) return 0;
+    if (!x || !w_codes || !w_alpha || !y || !codebook) return ANTQ_EINVAL;
+    if (dtype != ANTQ_F16 && dtype != ANTQ_BF16) return ANTQ_ENOTSUP;
+    if ((flags & ANTQ_FLAG_OVP) && info->n_entries > info->n_normal) return ANTQ_ENOTSUP;      // pair bytes: decode first
+    if (info->n_entries > 16 || K % BK || N % BN || K == 0 || M > 0x7fffffffLL / 2 || N > 0x7fffffffLL / 2) return ANTQ_ENOTSUP;
+    if ((uintptr_t)x % 16 || (uintptr_t)y % 16 || (uintptr_t)w_codes % 16) return ANTQ_EALIGN;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return ANTQ_ENOTSUP;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&map, dtype == ANTQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                           const_cast<void *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ANTQ_EINVAL;
+    GemmParams p;
+    p.codes = w_codes; p.alpha = w_alpha; p.bias = bias; p.y = y; p.cb = (const AntqCodebook *)codebook;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.m_tiles = (int)((M + BM - 1) / BM);
+    p.n_tiles = (int)(N / BN);
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    const int sms = antq_num_sms();
+    const int ctas = (int)(tiles < sms ? tiles : sms);
+    return dtype == ANTQ_F16 ? launch<__half>(map, p, ctas, (cudaStream_t)stream)
+                             : launch<__nv_bfloat16>(map, p, ctas, (cudaStream_t)stream);
+}

@@ -33,6 +33,7 @@ constexpr int kNS = 2 * kNC;              // two private stages per warp
 constexpr int kChunkMax = 4096;
 constexpr int kThreads = kNC * 32;
 constexpr unsigned kHalfFromMagic = 0x0C400000u;   // bits(1.5 * 2^k) - bits(2^(k - 24))
+constexpr int kListMax = 512;             // per-warp work list of elements to redo exactly (per chunk)
 
 struct PuParams {
     const void *x;
@@ -202,6 +203,24 @@ __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const P
     return PuIO<T>::pack(o);
 }
 
+// Which elements of a vector need the exact redo (bit e), recomputed with the closed form's own tests -- unrolled, in
+// registers (an indexed loop over f[] would put the vector in local memory and make the redo latency-bound).
+template <typename T, bool UNIFORM>
+__device__ __forceinline__ unsigned pu_vec_mask(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC];
+    PuIO<T>::unpack(raw, f);
+    unsigned m = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) {
+        bool fl = false;
+        (void)pu_quant<UNIFORM>(f[e], r, K, tab, fl);
+        fl |= !(fabsf(f[e]) <= r.xl);
+        m |= (fl ? 1u : 0u) << e;
+    }
+    return m;
+}
+
 // Redo of the flagged elements of one vector (the vector itself has already been stored by this thread).
 template <typename T, bool UNIFORM>
 __device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, const PuExact X, const uint4 raw, const PuRow r,
@@ -209,14 +228,14 @@ __device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, co
     constexpr int VEC = PuIO<T>::VEC;
     float f[VEC];
     PuIO<T>::unpack(raw, f);
-#pragma unroll 1
-    for (int e = 0; e < VEC; e++) {
-        bool fl = !r.ok;
-        if (r.ok) {
-            (void)pu_quant<UNIFORM>(f[e], r, K, tab, fl);
-            fl |= !(fabsf(f[e]) <= r.xl);
-        }
-        if (fl) og[e] = pu_exact_elem<T>(cb, X, f[e], r.s);
+    unsigned m = r.ok ? pu_vec_mask<T, UNIFORM>(raw, r, K, tab) : ((1u << VEC) - 1u);
+    while (m) {
+        const int e = __ffs(m) - 1;
+        m &= m - 1;
+        float xf = f[0];
+#pragma unroll
+        for (int i = 1; i < VEC; i++) xf = e == i ? f[i] : xf;
+        og[e] = pu_exact_elem<T>(cb, X, xf, r.s);
     }
 }
 
@@ -237,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     float *x_lev = x_thr + ANTQ_MAX_GRID;
     uint64_t *full = reinterpret_cast<uint64_t *>(x_lev + ANTQ_MAX_GRID);
     unsigned *next_k = reinterpret_cast<unsigned *>(full + kNS);
+    unsigned short *redo_list = reinterpret_cast<unsigned short *>(next_k + 4) + (size_t)(threadIdx.x >> 5) * kListMax;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned c_begin = blockIdx.x * p.chunks_per_cta + min(blockIdx.x, p.chunks_rem);
@@ -347,10 +367,45 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             redo = 0xffffffffu;                                       // bad scale: every vector, literally
         }
         if (__any_sync(0xffffffffu, redo != 0)) {
-            for (int j = 0; j * 32 + lane < nvec; j++) {
-                if ((redo >> j) & 1u) {
-                    const int v = j * 32 + lane;
-                    pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
+            // Exact redo, dense: the flagged ELEMENTS of the whole chunk are compacted into a per-warp list and redone
+            // one per lane (a row with representable ties can flag a few percent of a chunk; redoing them vector by
+            // vector inside their owner lane serialised a warp for tens of microseconds: profiles/r02_notes.md).
+            unsigned long long em = 0;                                // bit 8 j + e: element e of vector j * 32 + lane
+            if (r.ok) {
+                for (int j = 0; j * 32 + lane < nvec; j++)
+                    if ((redo >> j) & 1u)
+                        em |= (unsigned long long)pu_vec_mask<T, UNIFORM>(sv[j * 32 + lane], r, K, tab) << (8 * j);
+            }
+            const int cnt = __popcll(em);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const bool overflow = !r.ok || total > kListMax;
+            if (!overflow) {
+                int pos = incl - cnt;
+                while (em) {
+                    const int b = __ffsll((long long)em) - 1;
+                    em &= em - 1;
+                    redo_list[pos++] = (unsigned short)((lane << 6) | b);
+                }
+                __syncwarp();          // list complete; the fast path's vector stores are ordered before the rewrites
+                for (int i = lane; i < total; i += 32) {
+                    const unsigned it = redo_list[i];
+                    const int v = (int)((it & 63u) >> 3) * 32 + (int)(it >> 6), e = (int)(it & 7u);
+                    const float xf = A::to_f32(reinterpret_cast<const T *>(sv + v)[e]);
+                    og[(long long)v * VEC + e] = pu_exact_elem<T>(cb, X, xf, r.s);
+                }
+                __syncwarp();          // the list is rewritten by this warp's next chunk
+            } else {
+                for (int j = 0; j * 32 + lane < nvec; j++) {
+                    if ((redo >> j) & 1u) {
+                        const int v = j * 32 + lane;
+                        pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
+                    }
                 }
             }
         }
@@ -403,7 +458,7 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
 
 template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_pu_stream_kernel<T, UNIFORM>;
-    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16;
+    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kNC * kListMax * 2;
     static unsigned long long configured = 0ull;                     // one bit per device ordinal
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -18,6 +18,7 @@
  *   antq_calibrate          search_mse + search_adaptive_numeric_type, fused   A/antquant/quant_modules.py:287-415
  *   antq_fakequant_backward autograd of _forward (QAT)                 A/antquant/quant_modules.py:535-551
  *   antq_encode_p4 / antq_decode_p4   the never-written `tensor_idx`   A/quant/quant_kernel.cu:18,49,61
+ *   antq_linear_p4          F.linear on fake-quantized operands, fused  A/antquant/quant_modules.py:642-646
  *   antq_host_*             the same forward for HOST buffers (copies inside)
  *
  * Conventions
@@ -170,6 +171,16 @@ int antq_calibrate(const void *x, int64_t rows, int64_t cols, int dtype, int alp
                    const float *ratios, int n_cand, const void *const *codebooks, const antq_codebook_info *const *infos,
                    const int *flags_per_codebook, int n_cb, float *alpha_out, float *mse_out, int *best_index_out,
                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- dequant-fused Linear on the tensor cores (tcgen05.mma, accumulators in tensor memory, TMA for x) ----
+ * y[M, N] = x[M, K] . dequant(W)[N, K]^T + bias[N], W given as P4 codes [N, K / 2] + alpha[N] (antq_encode_p4).
+ * Replaces  F.linear(quant_input(x), quant_weight(W), bias)  of LinearQuantizer.forward
+ * (A/antquant/quant_modules.py:642-646; torch.addmm in O/antquant/quant_modules.py:379).
+ * dtype: ANTQ_F16 or ANTQ_BF16 (x, bias, y); fp32 accumulation; K % 64 == 0, N % 128 == 0, grid <= 16 entries,
+ * no outlier-victim pairs (decode those first): otherwise ANTQ_ENOTSUP and the caller keeps the unfused path. */
+int antq_linear_p4(const void *x, const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M,
+                   int64_t N, int64_t K, int dtype, const void *codebook, const antq_codebook_info *info, int flags,
+                   void *stream);
 
 /* ---- host-buffer path (what a CPU caller of the reference would use) ---- */
 typedef struct antq_host_ctx antq_host_ctx;

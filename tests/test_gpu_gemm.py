@@ -1,0 +1,76 @@
+"""Dequant-fused Linear on tcgen05 (antq_linear_p4) against F.linear on the fake-quantized operands
+(A/antquant/quant_modules.py:642-646): a one-hot activation makes every output a single product, so the decode LUT, the
+128-byte-swizzled operand layout, the UMMA descriptors and the tensor-memory epilogue are checked BIT-EXACTLY; random
+activations are checked within the fp32-accumulate tolerance written below."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import antq_oracle as orc
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def antq():
+    import antq as m
+    return m
+
+
+def _weights(antq, N, K, kind, signed, dtype, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(dtype).to(dev())
+    if not signed:
+        w = w.abs()
+    grid = orc.ant_grid(kind, 4, signed)
+    cb = antq.prepare_codebook(torch.from_numpy(grid).to(dev()))
+    alpha = (w.float().abs().amax(1) * 0.9).contiguous()
+    wq = antq.fakequant(w, alpha, cb, True)
+    codes, bad = antq.encode_p4(w, alpha, cb, True)
+    assert int(bad.item()) == 0
+    return w, wq, codes, alpha, cb
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind,signed", [("flint", True), ("pot", True), ("flint", False)])
+def test_linear_p4_one_hot_is_bit_exact(antq, kind, signed, dtype):
+    N, K = 256, 256
+    w, wq, codes, alpha, cb = _weights(antq, N, K, kind, signed, dtype, 1)
+    x = torch.eye(K, dtype=dtype, device=dev())                        # y[m, n] = W_q[n, m]: one product per output
+    y = antq.linear_p4(x, codes, alpha, cb, N)
+    # every flint / pot level is exact in fp16 and bf16, so level * s rounds once on both sides
+    assert torch.equal(y.view(torch.int16), wq.t().contiguous().view(torch.int16))
+    bias = torch.randn(N, device=dev()).to(dtype)
+    yb = antq.linear_p4(x, codes, alpha, cb, N, bias=bias)
+    ref = (wq.t().float() + bias.float()).to(dtype)
+    assert float((yb.float() - ref.float()).abs().max()) <= float(ref.float().abs().max()) * 2.0 ** -7
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (300, 256, 1024), (77, 128, 4096), (2048, 4096, 4096)])
+def test_linear_p4_matches_f_linear(antq, M, N, K, dtype):
+    w, wq, codes, alpha, cb = _weights(antq, N, K, "flint", True, dtype, 2)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(M, K, generator=g).to(dtype).to(dev())
+    bias = (torch.randn(N, generator=g) * 0.1).to(dtype).to(dev())
+    y = antq.linear_p4(x, codes, alpha, cb, N, bias=bias)
+    ref = F.linear(x.float(), wq.float(), bias.float())               # fp32 reference on the fake-quantized operands
+    err = (y.float() - ref).norm() / ref.norm()
+    # one rounding of the output to 16 bits (2^-11 fp16 / 2^-8 bf16 relative) dominates; fp32 accumulation is below it
+    tol = 1.5e-3 if dtype == torch.float16 else 6e-3
+    assert float(err) < tol, float(err)
+    lib = F.linear(x, wq, bias)                                        # cuBLAS on the same operands, same dtype
+    err_lib = (lib.float() - ref).norm() / ref.norm()
+    assert float(err) < 2.0 * float(err_lib) + 1e-4, (float(err), float(err_lib))
+    # 3-D activations keep their leading shape
+    y3 = antq.linear_p4(x.view(1, M, K), codes, alpha, cb, N, bias=bias)
+    assert y3.shape == (1, M, N) and torch.equal(y3.view(M, N), y)
+
+
+def test_linear_p4_declines_what_it_cannot_do(antq):
+    w, wq, codes, alpha, cb = _weights(antq, 128, 64, "flint", True, torch.float16, 4)
+    x = torch.randn(8, 64, device=dev())
+    with pytest.raises(RuntimeError):
+        antq.linear_p4(x, codes, alpha, cb, 128)                       # fp32 activations: unsupported, loudly

@@ -27,8 +27,8 @@ for name, shape, is_input, dt in (("weight 4096x4096 fp16 per-channel", (4096, 4
         torch.cuda.synchronize(); t_init = time.perf_counter() - t0
     for _ in range(3): q(x)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(20): q(x)
-    torch.cuda.synchronize(); t_fwd = (time.perf_counter() - t0) / 20
+    for _ in range(200): q(x)
+    torch.cuda.synchronize(); t_fwd = (time.perf_counter() - t0) / 200
     out.append({"tensor": name, "chosen": q.mode, "init_ms": round(t_init * 1e3, 2), "steady_forward_us": round(t_fwd * 1e6, 1),
                 "elements": x.numel()})
 # per-call host overhead of the module API: a tensor so small that the kernel is negligible, 2000 back-to-back calls
