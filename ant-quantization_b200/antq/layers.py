@@ -14,6 +14,12 @@ import torch.nn.functional as F
 
 
 CACHE_WEIGHTS = os.environ.get("ANTQ_CACHE_WEIGHTS", "1") != "0"
+# Opt-in: eval-mode LinearQuantizer layers with a 4-bit weight and fp16 / bf16 activations keep the
+# weight as packed 4-bit codes + one alpha per output channel and run  y = x_q . dequant(W)^T + b  in ONE tcgen05 kernel
+# (antq_linear_p4) instead of fake-quantizing the weight to fp16 and calling cuBLAS.  Numerically this is F.linear on
+# the fake-quantized operands up to fp32 accumulation order (tests/test_gpu_gemm.py); off by default because the
+# reference's F.linear rounds differently in the last bit.
+FUSED_LINEAR = os.environ.get("ANTQ_FUSED_LINEAR", "0") == "1"
 
 
 def _copy_param(t):
@@ -51,6 +57,7 @@ def make_layers(TensorQuantizer):
         # `antq.layers.CACHE_WEIGHTS = False` (ANTQ_CACHE_WEIGHTS=0) for the reference's behaviour exactly.
         def invalidate_weight_cache(self):
             self._wq_key = self._wq_val = None
+            self._wc_key = self._wc_val = None
 
         def train(self, mode=True):
             self.invalidate_weight_cache()
@@ -121,7 +128,38 @@ def make_layers(TensorQuantizer):
             self.quant_weight.alpha.data = torch.ones([self.out_features, 1])
             self._set_weight_bias(linear)
 
+        def _weight_codes(self, input):
+            """(codes, alpha, codebook) of the fake-quantized weight, cached like the fp tensor (same key), or None when
+            the fused kernel does not apply: OliVe outlier pairs, grids of more than 16 entries, shapes it declines,
+            or a weight whose fake-quant values the codes would not reproduce bit for bit (antq_encode_p4 counts them)."""
+            from . import ops
+            q, w = self.quant_weight, self.weight
+            if q.mode == "base" or not q.is_enable or not q.is_enable_weight or q._ovp or not w.is_cuda:
+                return None
+            if not q._is_inited():
+                q(w, input)                                            # calibrates exactly as the unfused path would
+            key = self._weight_key()
+            if key is None:
+                return None
+            if key == getattr(self, "_wc_key", None):
+                return self._wc_val
+            val = None
+            cb = q._codebook(w.device)
+            if cb.info.n_entries <= 16 and w.shape[1] % 64 == 0 and w.shape[0] % 128 == 0 and w.dtype in (torch.float16, torch.bfloat16):
+                codes, bad = ops.encode_p4(w.detach(), q.alpha, cb, True)
+                if int(bad.item()) == 0:                               # one synchronisation, when the cache is filled
+                    val = (codes, q.alpha.detach().reshape(-1).float().contiguous(), cb)
+            self._wc_key, self._wc_val = key, val
+            return val
+
         def forward(self, input):
+            if FUSED_LINEAR and not self.training and input.is_cuda and input.dtype in (torch.float16, torch.bfloat16) \
+                    and not (torch.is_grad_enabled() and input.requires_grad):
+                pack = self._weight_codes(input)
+                if pack is not None:
+                    from . import ops
+                    xq = self.quant_input(input, self.weight)
+                    return ops.linear_p4(xq, pack[0], pack[1], pack[2], self.out_features, self.bias)
             input, weight = self._quantized(input)
             return F.linear(input, weight, self.bias)
 

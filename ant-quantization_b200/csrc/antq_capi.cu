@@ -104,10 +104,11 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
         if (pu && rows > 1 && cols % vec == 0) return 5;
         return ANTQ_ENOTSUP;
     }
-    // the compare chain (packed 16-bit arithmetic, two elements per instruction) wins up to 15 thresholds after folding
-    // signs -- every 4-bit grid, signed 5-bit, OliVe's two-phase chain; beyond that the closed form does (fp32 per
-    // element, but independent of the number of levels): unsigned 5-bit, 6 to 8 bit  (measured: profiles/r02_notes.md)
-    if (chain && (nt <= 15 || !pu)) return 1;
+    // the compare chain (packed 16-bit arithmetic, two elements per instruction) wins while it is short: <= 7 thresholds
+    // after folding signs = every signed 4-bit grid and OliVe's two-phase chain (13.7-15 us per 4096^2 fp16).  Beyond
+    // that the closed form does (fp32 per element but independent of the number of levels, 17-20 us): unsigned 4-bit,
+    // 5 to 8 bit.  Measured side by side in profiles/r02_notes.md.
+    if (chain && (nt <= 7 || !pu)) return 1;
     if (pu && long_rows) return 4;
     if (chain) return 1;
     const bool short_rows = info && !codes && aligned && rows > 1 && cols < kRowsMinCols && cols % vec == 0;

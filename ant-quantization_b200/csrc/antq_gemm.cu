@@ -13,13 +13,14 @@
 // the epilogue:  y = fl16(acc * s_n + bias).  Against F.linear on the fake-quantized operands this differs by fp32
 // accumulation order and one 16-bit rounding per weight (2^-12 relative, uncorrelated): tolerance in the test.
 //
-// Structure (one CTA per SM, persistent over 128 x 128 output tiles, BK = 64, kStages-deep shared-memory ring):
-//   warp 4      TMA producer: x tiles [128 x 64] by cp.async.bulk.tensor.2d (128-byte swizzle) -> full[stage]
+// Structure (one CTA per SM, persistent over 256 x 128 output tiles, BK = 64, kStages-deep shared-memory ring):
+//   warp 4      TMA producer: x tiles [256 x 64] by cp.async.bulk.tensor.2d (128-byte swizzle) -> full[stage]
 //   warps 6-9   weight decoders: thread = one output channel of the tile; 32 bytes of codes -> 64 operand values through
 //               a 16-entry byte LUT held in registers (PRMT), written in the same K-major 128-byte-swizzled layout
 //               -> fence.proxy.async -> full[stage]
-//   warp 5      MMA issuer: one lane issues 4 x tcgen05.mma (M128 N128 K16, kind::f16) per stage into one of two
-//               128-column accumulators in tensor memory; tcgen05.commit frees the stage / publishes the accumulator
+//   warp 5      MMA issuer: one lane issues 2 x 4 tcgen05.mma (M128 N128 K16, kind::f16) per stage -- the two M-halves of
+//               the 256-row x tile share the decoded W tile, which halves the decode work per flop -- into one of two
+//               2 x 128-column accumulators in tensor memory; tcgen05.commit frees the stage / publishes the accumulator
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, bias, 16-bit stores; overlaps the next
 //               tile's main loop through the second accumulator
 // SASS evidence: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld): profiles/r02_gemm_sass.txt.
@@ -30,12 +31,13 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 5;
-constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;            // bytes (16-bit operands)
+constexpr int BM = 256, BN = 128, BK = 64;                            // BM = two UMMA M-halves of 128 sharing one decoded W tile
+constexpr int kStages = 4;
+constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;            // bytes (16-bit operands): 32 KiB + 16 KiB
 constexpr int kEpiWarps = 4, kTmaWarp = 4, kMmaWarp = 5, kDecWarp0 = 6, kDecWarps = 4;
 constexpr int kThreads = (kDecWarp0 + kDecWarps) * 32;                 // 320
-constexpr int kTmemCols = 256;                                         // two fp32 accumulators of 128 columns
+constexpr int kTmemCols = 512;                                         // 2 (double buffer) x 2 (M-halves) x 128 fp32 columns
+constexpr int kAccCols = 2 * BN;                                       // columns of one accumulator buffer
 
 struct GemmParams {
     const unsigned char *codes;       // [N, K / 2]
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         if (lane == 0) {
             // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A / B format << 7 / << 10, K-major both, N >> 3 << 17, M >> 4 << 24
             const uint32_t idesc = (1u << 4) | (Op16<T>::kFormat << 7) | (Op16<T>::kFormat << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(BM >> 4) << 24);
+                                   ((uint32_t)(128 >> 4) << 24);
             int stage = 0;
             unsigned phase = 0;
             int it = 0;
@@ -199,15 +201,18 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
                 const int acc = it & 1;
                 mbar_wait(tmem_empty + acc, ((it >> 1) & 1) ^ 1u);                 // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(full + stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t adesc = umma_desc(antq_smem_u32(smem_a + stage * kStageA));
                     const uint64_t bdesc = umma_desc(antq_smem_u32(smem_b + stage * kStageB));
 #pragma unroll
-                    for (int j = 0; j < BK / 16; j++)                               // K = 16 per instruction = 32 bytes = 2 x 16 B
-                        umma_f16(d_tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0);
+                    for (int h = 0; h < 2; h++)                                     // two M-halves reuse the decoded W tile
+#pragma unroll
+                        for (int j = 0; j < BK / 16; j++)                           // K = 16 per instruction = 32 bytes = 2 x 16 B
+                            umma_f16(d_tmem + (uint32_t)(h * BN), adesc + (uint64_t)(h * (128 * 128 / 16) + 2 * j),
+                                     bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0);
                     umma_commit(empty + stage);                                     // frees the stage when these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -228,26 +233,37 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         const int sw = n_local & 7;
         int stage = 0;
         unsigned phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int n_blk = t / p.m_tiles;
-            const unsigned char *crow = p.codes + (size_t)(n_blk * BN + n_local) * (size_t)(p.K / 2);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const uint4 c0 = __ldg(reinterpret_cast<const uint4 *>(crow + kb * (BK / 2)));
-                const uint4 c1 = __ldg(reinterpret_cast<const uint4 *>(crow + kb * (BK / 2)) + 1);
-                mbar_wait(empty + stage, phase ^ 1u);
-                unsigned char *dst = smem_b + stage * kStageB + row_off;
-                const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {                                       // one 32-bit word = 8 codes = one 16-byte chunk
-                    uint4 v;
-                    lut4(w[j], lo, hi, v.x, v.y);
-                    lut4(w[j] >> 16, lo, hi, v.z, v.w);
-                    *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> tensor-core reads
-                mbar_arrive(full + stage);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        // the codes of the NEXT k-block are in flight while the current one is decoded (a global load issued and
+        // consumed in the same iteration exposed ~1 us of latency per stage)
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const long long total_it = (long long)my_tiles * num_kb;
+        int f_tile = blockIdx.x, f_kb = 0;                                          // position of the next fetch
+        auto fetch = [&](uint4 &a, uint4 &b) {
+            if (f_tile < num_tiles) {
+                const int n_blk = f_tile / p.m_tiles;
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.codes + (size_t)(n_blk * BN + n_local) * (size_t)(p.K / 2) + f_kb * (BK / 2));
+                a = __ldg(src); b = __ldg(src + 1);
+                if (++f_kb == num_kb) { f_kb = 0; f_tile += gridDim.x; }
             }
+        };
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, n0 = c0, n1 = c0;
+        fetch(c0, c1);
+        for (long long it = 0; it < total_it; it++) {
+            fetch(n0, n1);
+            mbar_wait(empty + stage, phase ^ 1u);
+            unsigned char *dst = smem_b + stage * kStageB + row_off;
+            const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {                                           // one 32-bit word = 8 codes = one 16-byte chunk
+                uint4 v;
+                lut4(w[j], lo, hi, v.x, v.y);
+                lut4(w[j] >> 16, lo, hi, v.z, v.w);
+                *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> tensor-core reads
+            mbar_arrive(full + stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            c0 = n0; c1 = n1;
         }
     } else {
         // ------------------------------ epilogue (warps 0-3 = tensor-memory lanes 32 w .. 32 w + 31) ------------------------------
@@ -265,22 +281,25 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
             asm volatile("bar.sync 1, 128;" ::: "memory");                          // the epilogue warps only
             mbar_wait(tmem_full + acc, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int m = m_blk * BM + warp * 32 + lane;
-            T *yrow = reinterpret_cast<T *>(p.y) + (size_t)m * p.N + (size_t)n_blk * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c), v);
-                if (m < p.M) {
+            for (int h = 0; h < 2; h++) {
+                const int m = m_blk * BM + h * 128 + warp * 32 + lane;
+                T *yrow = reinterpret_cast<T *>(p.y) + (size_t)m * p.N + (size_t)n_blk * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * kAccCols + h * BN + c), v);
+                    if (m < p.M) {
 #pragma unroll
-                    for (int q = 0; q < 32; q += 8) {
-                        uint4 o;
-                        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+                        for (int q = 0; q < 32; q += 8) {
+                            uint4 o;
+                            uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2)
-                            ow[e >> 1] = Op16<T>::pack(__fmaf_rn(__uint_as_float(v[q + e]), sc[c + q + e], bs[c + q + e]),
-                                                       __fmaf_rn(__uint_as_float(v[q + e + 1]), sc[c + q + e + 1], bs[c + q + e + 1]));
-                        *reinterpret_cast<uint4 *>(yrow + c + q) = o;
+                            for (int e = 0; e < 8; e += 2)
+                                ow[e >> 1] = Op16<T>::pack(__fmaf_rn(__uint_as_float(v[q + e]), sc[c + q + e], bs[c + q + e]),
+                                                           __fmaf_rn(__uint_as_float(v[q + e + 1]), sc[c + q + e + 1], bs[c + q + e + 1]));
+                            *reinterpret_cast<uint4 *>(yrow + c + q) = o;
+                        }
                     }
                 }
             }

@@ -105,7 +105,10 @@ def test_fused_backward(antq, per_row, dtype):
     out = antq.fakequant(x, alpha, cb, per_row)
     gmax = float(grid.max())
     gx, ga = antq.fakequant_backward(g, x, out, alpha, gmax, per_row)
-    s = (alpha / np.float32(gmax)).reshape(-1, 1) if per_row else alpha / np.float32(gmax)
+    # tensor / 0-dim CUDA tensor = IEEE division, as in the reference (`alpha / torch.max(quant_grid)`); dividing by a
+    # Python / numpy scalar would silently become a multiplication by the rounded reciprocal
+    gm = torch.tensor(gmax, dtype=torch.float32, device=dev())
+    s = (alpha / gm).reshape(-1, 1) if per_row else alpha / gm
     gx_ref = ((g.float() * s) / s).to(dtype)                                  # autograd's mul-then-div, bit for bit
     assert torch.equal(gx.view(torch.int16 if dtype == torch.float16 else torch.int32),
                        gx_ref.view(torch.int16 if dtype == torch.float16 else torch.int32))

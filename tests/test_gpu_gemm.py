@@ -74,3 +74,40 @@ def test_linear_p4_declines_what_it_cannot_do(antq):
     x = torch.randn(8, 64, device=dev())
     with pytest.raises(RuntimeError):
         antq.linear_p4(x, codes, alpha, cb, 128)                       # fp32 activations: unsupported, loudly
+
+
+def test_linear_quantizer_fused_path():
+    """LinearQuantizer with antq.layers.FUSED_LINEAR: the weight is cached as packed codes and the layer output matches
+    the unfused layer (fake-quantized fp16 weight + cuBLAS) to accumulation-order noise; training mode, fp32
+    activations and OliVe outlier pairs keep the unfused path."""
+    from host_util import run
+    res, _ = run("ant", r'''
+import antq.layers as L
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+lin = nn.Linear(1024, 512).to(dev).half()
+q = LinearQuantizer(mode="flint", wbit=4, abit=4, args=mkargs("flint"))
+q.set_param(lin)
+q = q.to(dev).eval()
+q.quant_weight.enable_quantization("w"); q.quant_input.enable_quantization("a")
+x = torch.randn(4, 96, 1024, device=dev).half()
+with torch.no_grad():
+    y0 = q(x)                                    # calibrates, unfused
+    y1 = q(x)
+    L.FUSED_LINEAR = True
+    y2 = q(x)
+    pack = q._wc_val
+    y3 = q(x)
+    hit = q._wc_val is pack and pack is not None
+    codes_bytes = pack[0].numel() if pack is not None else -1
+    q.train(); yt = q(x); q.eval()                # training mode: unfused, cache dropped
+    dropped = q._wc_val is None
+    y4 = q(x.float().half())
+    L.FUSED_LINEAR = False
+rel = float((y2.float() - y1.float()).norm() / y1.float().norm())
+RESULT.update(rel=rel, hit=bool(hit), same=bool(torch.equal(y2, y3) and torch.equal(y3, y4)), codes_bytes=codes_bytes,
+              train_unfused=bool(torch.equal(yt, y1)), dropped=bool(dropped), shape=list(y2.shape))
+''', timeout=600)
+    assert res["shape"] == [4, 96, 512] and res["hit"] and res["same"] and res["dropped"] and res["train_unfused"], res
+    assert res["codes_bytes"] == 512 * 1024 // 2, res
+    assert res["rel"] < 2e-3, res
