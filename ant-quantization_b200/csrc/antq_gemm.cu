@@ -246,24 +246,34 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
                 if (++f_kb == num_kb) { f_kb = 0; f_tile += gridDim.x; }
             }
         };
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, n0 = c0, n1 = c0;
-        fetch(c0, c1);
-        for (long long it = 0; it < total_it; it++) {
-            fetch(n0, n1);
-            mbar_wait(empty + stage, phase ^ 1u);
-            unsigned char *dst = smem_b + stage * kStageB + row_off;
-            const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        // kPrefetch k-blocks of codes are in flight while the current one is decoded: a global load issued and consumed in
+        // the same iteration exposed ~1 us of latency per stage, and one block ahead still left the decoders on the
+        // long scoreboard 5 cycles per issue (profiles/r02_notes.md)
+        constexpr int kPrefetch = 4;
+        uint4 pa[kPrefetch], pb[kPrefetch];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {                                           // one 32-bit word = 8 codes = one 16-byte chunk
-                uint4 v;
-                lut4(w[j], lo, hi, v.x, v.y);
-                lut4(w[j] >> 16, lo, hi, v.z, v.w);
-                *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
+        for (int u = 0; u < kPrefetch; u++) { pa[u] = make_uint4(0, 0, 0, 0); pb[u] = pa[u]; fetch(pa[u], pb[u]); }
+        for (long long it = 0; it < total_it; it += kPrefetch) {
+#pragma unroll
+            for (int u = 0; u < kPrefetch; u++) {
+                if (it + u < total_it) {
+                    const uint4 c0 = pa[u], c1 = pb[u];
+                    fetch(pa[u], pb[u]);                                            // the block kPrefetch ahead
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    unsigned char *dst = smem_b + stage * kStageB + row_off;
+                    const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {                                   // one 32-bit word = 8 codes = one 16-byte chunk
+                        uint4 v;
+                        lut4(w[j], lo, hi, v.x, v.y);
+                        lut4(w[j] >> 16, lo, hi, v.z, v.w);
+                        *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> tensor-core reads
+                    mbar_arrive(full + stage);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> tensor-core reads
-            mbar_arrive(full + stage);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            c0 = n0; c1 = n1;
         }
     } else {
         // ------------------------------ epilogue (warps 0-3 = tensor-memory lanes 32 w .. 32 w + 31) ------------------------------

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    struct Geo { long long base; int nvec, tail; float alpha; };
+    struct Geo { long long base; int nvec, tail; unsigned row; float alpha; };
     auto geo_of = [&](int k) {
         Geo g;
         const unsigned c = c_begin + (unsigned)k;
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
         g.nvec = n_el / VEC;
         g.tail = n_el - g.nvec * VEC;
         g.base = (long long)row * p.cols + col0;
+        g.row = row;
         g.alpha = 0.0f;
         return g;
     };
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             }
         }
         // the row's alpha travels with the request: its latency hides behind the bulk copy
-        g.alpha = __ldg(p.alpha + (p.alpha_per_row ? (g.base / p.cols) : 0));
+        g.alpha = __ldg(p.alpha + (p.alpha_per_row ? g.row : 0u));
     };
     auto claim = [&]() {
         int k = 0;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     };
 
     Geo cur;
-    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.alpha = 0.0f;
+    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.row = 0; cur.alpha = 0.0f;
     int k = claim();
     if (k < n) {
         cur = geo_of(k);

@@ -175,6 +175,28 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def scatter_forward_gather(dist, fn, x_all, x_loc, y_all, rank):
+    """One batch-sharded step: rank 0 scatters one sample per rank, every rank runs `fn` on its shard, the outputs are
+    all-gathered (north_star: "NCCL only to scatter inputs and gather logits").  dist = None: single process."""
+    if dist is not None:
+        dist.scatter(x_loc, list(x_all.unsqueeze(1).unbind(0)) if rank == 0 else None, src=0)
+    else:
+        x_loc.copy_(x_all)
+    y = fn(x_loc)
+    if dist is not None:
+        dist.all_gather_into_tensor(y_all, y.contiguous())
+    else:
+        y_all.copy_(y)
+    return y_all
+
+
+def shard_rows(n_rows, world, rank):
+    """Row range of `rank` when one tensor of n_rows rows is sharded over `world` ranks (strong scaling)."""
+    per = (n_rows + world - 1) // world
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows)
+
+
 class OPTLayer:
     """Built lazily (needs torch): an OPT-6.7B decoder layer, the six nn.Linear the OliVe scripts quantize per layer
     (O/llm/run_clm.py:603-613)."""
@@ -251,7 +273,8 @@ def run_extras(torch, antq, dist, device, rank, world, local, graph, cb, peak):
     # ---- (2) strong scaling: ONE 16384 x 16384 fp16 tensor, rows sharded over the ranks ----
     try:
         NS = 16384
-        rows = NS // world
+        lo_r, hi_r = shard_rows(NS, world, rank)
+        rows = hi_r - lo_r
         g = torch.Generator(device=device).manual_seed(99)
         xs = (torch.randn(rows, NS, device=device, generator=g) * 0.02).to(torch.float16)
         al = (xs.float().abs().amax(1) * 0.9).contiguous()
@@ -328,17 +351,12 @@ def run_extras(torch, antq, dist, device, rank, world, local, graph, cb, peak):
         x_loc = torch.empty(1, S, H, device=device, dtype=torch.float16)
         y_all = torch.empty(world, S, H, device=device, dtype=torch.float16)
 
-        def step():
-            if dist is not None:
-                dist.scatter(x_loc, list(x_all.unsqueeze(1).unbind(0)) if rank == 0 else None, src=0)
-            else:
-                x_loc.copy_(x_all)
+        def fwd(xl):
             with torch.no_grad():
-                y = q(x_loc)
-            if dist is not None:
-                dist.all_gather_into_tensor(y_all, y.contiguous())
-            else:
-                y_all.copy_(y)
+                return q(xl)
+
+        def step():
+            scatter_forward_gather(dist, fwd, x_all, x_loc, y_all, rank)
         for _ in range(3):
             step()
         sync_all()
