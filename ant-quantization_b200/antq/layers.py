@@ -20,6 +20,7 @@ CACHE_WEIGHTS = os.environ.get("ANTQ_CACHE_WEIGHTS", "1") != "0"
 # the fake-quantized operands up to fp32 accumulation order (tests/test_gpu_gemm.py); off by default because the
 # reference's F.linear rounds differently in the last bit.
 FUSED_LINEAR = os.environ.get("ANTQ_FUSED_LINEAR", "0") == "1"
+FUSED_MIN_ROWS = int(os.environ.get("ANTQ_FUSED_MIN_ROWS", "256"))
 
 
 def _copy_param(t):
@@ -145,7 +146,7 @@ def make_layers(TensorQuantizer):
                 return self._wc_val
             val = None
             cb = q._codebook(w.device)
-            if cb.info.n_entries <= 16 and w.shape[1] % 64 == 0 and w.shape[0] % 128 == 0 and w.dtype in (torch.float16, torch.bfloat16):
+            if cb.info.n_entries <= 16 and w.shape[1] % 64 == 0 and w.shape[0] % 256 == 0 and w.dtype in (torch.float16, torch.bfloat16):
                 codes, bad = ops.encode_p4(w.detach(), q.alpha, cb, True)
                 if int(bad.item()) == 0:                               # one synchronisation, when the cache is filled
                     val = (codes, q.alpha.detach().reshape(-1).float().contiguous(), cb)
@@ -153,7 +154,10 @@ def make_layers(TensorQuantizer):
             return val
 
         def forward(self, input):
+            # (small batches -- fewer rows than one 256-row tile per SM wave -- are latency-bound in the fused kernel:
+            #  they keep the cached fp16 weight + cuBLAS)
             if FUSED_LINEAR and not self.training and input.is_cuda and input.dtype in (torch.float16, torch.bfloat16) \
+                    and input.numel() // max(input.shape[-1], 1) >= FUSED_MIN_ROWS \
                     and not (torch.is_grad_enabled() and input.requires_grad):
                 pack = self._weight_codes(input)
                 if pack is not None:

@@ -13,16 +13,16 @@
 // the epilogue:  y = fl16(acc * s_n + bias).  Against F.linear on the fake-quantized operands this differs by fp32
 // accumulation order and one 16-bit rounding per weight (2^-12 relative, uncorrelated): tolerance in the test.
 //
-// Structure (one CTA per SM, persistent over 256 x 128 output tiles, BK = 64, kStages-deep shared-memory ring):
+// Structure (one CTA per SM, persistent over 256 x 256 output tiles, BK = 64, kStages-deep shared-memory ring):
 //   warp 4      TMA producer: x tiles [256 x 64] by cp.async.bulk.tensor.2d (128-byte swizzle) -> full[stage]
-//   warps 6-9   weight decoders: thread = one output channel of the tile; 32 bytes of codes -> 64 operand values through
+//   warps 6-13  weight decoders: thread = one of the tile's 256 output channels; 32 bytes of codes -> 64 operand values through
 //               a 16-entry byte LUT held in registers (PRMT), written in the same K-major 128-byte-swizzled layout
 //               -> fence.proxy.async -> full[stage]
-//   warp 5      MMA issuer: one lane issues 2 x 4 tcgen05.mma (M128 N128 K16, kind::f16) per stage -- the two M-halves of
-//               the 256-row x tile share the decoded W tile, which halves the decode work per flop -- into one of two
-//               2 x 128-column accumulators in tensor memory; tcgen05.commit frees the stage / publishes the accumulator
-//   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, bias, 16-bit stores; overlaps the next
-//               tile's main loop through the second accumulator
+//   warp 5      MMA issuer: one lane issues 2 x 4 tcgen05.mma (M128 N256 K16, kind::f16) per stage -- the two M-halves of
+//               the 256-row x tile share the decoded W tile, which halves the decode work per flop -- into the 2 x 256
+//               fp32 columns of tensor memory; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), scale, bias, 16-bit stores (the accumulator fills
+//               all 512 columns, so the next tile's first MMA waits for it: ~5 % of a tile)
 // SASS evidence: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld): profiles/r02_gemm_sass.txt.
 #include <cuda.h>
 #include <stdio.h>
@@ -31,13 +31,16 @@
 
 namespace {
 
-constexpr int BM = 256, BN = 128, BK = 64;                            // BM = two UMMA M-halves of 128 sharing one decoded W tile
-constexpr int kStages = 4;
-constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;            // bytes (16-bit operands): 32 KiB + 16 KiB
-constexpr int kEpiWarps = 4, kTmaWarp = 4, kMmaWarp = 5, kDecWarp0 = 6, kDecWarps = 4;
-constexpr int kThreads = (kDecWarp0 + kDecWarps) * 32;                 // 320
-constexpr int kTmemCols = 512;                                         // 2 (double buffer) x 2 (M-halves) x 128 fp32 columns
-constexpr int kAccCols = 2 * BN;                                       // columns of one accumulator buffer
+// 256 x 256 output tile per CTA: two UMMA M-halves of 128 rows share one decoded W tile of 256 channels.  The x tile is
+// re-read by every CTA that owns another column block, so its L2 -> SM traffic is M K (N / BN) 2 bytes: with BN = 128 that
+// was 7.3 TB/s at 0.57 of the tensor peak -- the kernel was L2-bandwidth-bound, not decode- or MMA-bound (r02 notes).
+constexpr int BM = 256, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;            // bytes (16-bit operands): 32 KiB + 32 KiB
+constexpr int kEpiWarps = 4, kTmaWarp = 4, kMmaWarp = 5, kDecWarp0 = 6, kDecWarps = 8;   // 2 decoder warps per scheduler
+constexpr int kThreads = (kDecWarp0 + kDecWarps) * 32;                 // 448
+constexpr int kTmemCols = 512;                                         // 2 (M-halves) x 256 fp32 columns: all of tensor memory
+constexpr int kAccCols = 0;                                            // single accumulator buffer
 
 struct GemmParams {
     const unsigned char *codes;       // [N, K / 2]
@@ -152,15 +155,15 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
     uint64_t *tmem_empty = tmem_full + 2;                                  // [2]
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *s_scale = reinterpret_cast<float *>(tmem_base_slot + 4);        // [2][BN] alpha / max(grid) of the tile's channels
-    float *s_bias = s_scale + 2 * BN;                                      // [2][BN]
+    float *s_bias = s_scale + 2 * BN;                                      // [2][BN] (only buffer 0 is used with one accumulator)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.K / BK;
     const int num_tiles = p.m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(full + s, 1 + kDecWarps * 32); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, kEpiWarps * 32); }
+        for (int s = 0; s < kStages; s++) { mbar_init(full + s, 1 + kDecWarps); mbar_init(empty + s, 1); }   // one arrival per decoder WARP
+        for (int a = 0; a < 2; a++) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kTmaWarp) {
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
             unsigned phase = 0;
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
-                const int acc = it & 1;
-                mbar_wait(tmem_empty + acc, ((it >> 1) & 1) ^ 1u);                 // the epilogue has drained this accumulator
+                const int acc = 0;
+                mbar_wait(tmem_empty + acc, (it & 1) ^ 1u);                        // the epilogue has drained the accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
                 for (int kb = 0; kb < num_kb; kb++) {
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         }
     } else if (warp >= kDecWarp0) {
         // ------------------------------ weight decoders ------------------------------
-        const int n_local = threadIdx.x - kDecWarp0 * 32;                           // 0..127: the tile's output channel
+        // thread = one of the tile's 256 output channels: 32 bytes of codes -> 8 x 16-byte operand chunks per k-block
+        const int n_local = threadIdx.x - kDecWarp0 * 32;
         uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int e = 0; e < 16; e++) {
@@ -233,8 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         const int sw = n_local & 7;
         int stage = 0;
         unsigned phase = 0;
-        // the codes of the NEXT k-block are in flight while the current one is decoded (a global load issued and
-        // consumed in the same iteration exposed ~1 us of latency per stage)
         const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const long long total_it = (long long)my_tiles * num_kb;
         int f_tile = blockIdx.x, f_kb = 0;                                          // position of the next fetch
@@ -247,9 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
             }
         };
         // kPrefetch k-blocks of codes are in flight while the current one is decoded: a global load issued and consumed in
-        // the same iteration exposed ~1 us of latency per stage, and one block ahead still left the decoders on the
-        // long scoreboard 5 cycles per issue (profiles/r02_notes.md)
-        constexpr int kPrefetch = 4;
+        // the same iteration exposed ~1 us of latency per stage (profiles/r02_notes.md)
+        constexpr int kPrefetch = 3;
         uint4 pa[kPrefetch], pb[kPrefetch];
 #pragma unroll
         for (int u = 0; u < kPrefetch; u++) { pa[u] = make_uint4(0, 0, 0, 0); pb[u] = pa[u]; fetch(pa[u], pb[u]); }
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
                         *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> tensor-core reads
-                    mbar_arrive(full + stage);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full + stage);                       // one arrival per warp
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -280,16 +282,16 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         const float gmax = p.cb->gmax;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
-            const int acc = it & 1;
+            const int acc = 0;
             const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
             float *sc = s_scale + acc * BN, *bs = s_bias + acc * BN;
-            {
-                const int n = n_blk * BN + threadIdx.x;                            // 128 epilogue threads: one channel each
-                sc[threadIdx.x] = __fdiv_rn(p.alpha[n], gmax);
-                bs[threadIdx.x] = p.bias ? Op16<T>::to_f32(reinterpret_cast<const T *>(p.bias)[n]) : 0.0f;
+            for (int c = threadIdx.x; c < BN; c += kEpiWarps * 32) {               // 128 epilogue threads, 256 channels
+                const int n = n_blk * BN + c;
+                sc[c] = __fdiv_rn(p.alpha[n], gmax);
+                bs[c] = p.bias ? Op16<T>::to_f32(reinterpret_cast<const T *>(p.bias)[n]) : 0.0f;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");                          // the epilogue warps only
-            mbar_wait(tmem_full + acc, (it >> 1) & 1);
+            mbar_wait(tmem_full + acc, it & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty + acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
             asm volatile("bar.sync 1, 128;" ::: "memory");                          // sc / bs of this accumulator may be rewritten
         }
     }

@@ -176,7 +176,7 @@ int antq_calibrate(const void *x, int64_t rows, int64_t cols, int dtype, int alp
  * y[M, N] = x[M, K] . dequant(W)[N, K]^T + bias[N], W given as P4 codes [N, K / 2] + alpha[N] (antq_encode_p4).
  * Replaces  F.linear(quant_input(x), quant_weight(W), bias)  of LinearQuantizer.forward
  * (A/antquant/quant_modules.py:642-646; torch.addmm in O/antquant/quant_modules.py:379).
- * dtype: ANTQ_F16 or ANTQ_BF16 (x, bias, y); fp32 accumulation; K % 64 == 0, N % 128 == 0, grid <= 16 entries,
+ * dtype: ANTQ_F16 or ANTQ_BF16 (x, bias, y); fp32 accumulation; K % 64 == 0, N % 256 == 0, grid <= 16 entries,
  * no outlier-victim pairs (decode those first): otherwise ANTQ_ENOTSUP and the caller keeps the unfused path. */
 int antq_linear_p4(const void *x, const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M,
                    int64_t N, int64_t K, int dtype, const void *codebook, const antq_codebook_info *info, int flags,

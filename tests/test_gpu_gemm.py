@@ -49,7 +49,7 @@ def test_linear_p4_one_hot_is_bit_exact(antq, kind, signed, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (300, 256, 1024), (77, 128, 4096), (2048, 4096, 4096)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 512), (300, 256, 1024), (77, 512, 4096), (2048, 4096, 4096)])
 def test_linear_p4_matches_f_linear(antq, M, N, K, dtype):
     w, wq, codes, alpha, cb = _weights(antq, N, K, "flint", True, dtype, 2)
     g = torch.Generator(device="cpu").manual_seed(3)
@@ -70,10 +70,10 @@ def test_linear_p4_matches_f_linear(antq, M, N, K, dtype):
 
 
 def test_linear_p4_declines_what_it_cannot_do(antq):
-    w, wq, codes, alpha, cb = _weights(antq, 128, 64, "flint", True, torch.float16, 4)
+    w, wq, codes, alpha, cb = _weights(antq, 256, 64, "flint", True, torch.float16, 4)
     x = torch.randn(8, 64, device=dev())
     with pytest.raises(RuntimeError):
-        antq.linear_p4(x, codes, alpha, cb, 128)                       # fp32 activations: unsupported, loudly
+        antq.linear_p4(x, codes, alpha, cb, 256)                       # fp32 activations: unsupported, loudly
 
 
 def test_linear_quantizer_fused_path():
@@ -86,6 +86,7 @@ import antq.layers as L
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 lin = nn.Linear(1024, 512).to(dev).half()
+L.FUSED_MIN_ROWS = 64
 q = LinearQuantizer(mode="flint", wbit=4, abit=4, args=mkargs("flint"))
 q.set_param(lin)
 q = q.to(dev).eval()
