@@ -245,3 +245,42 @@ RESULT.update(hit=bool(hit), same=bool(torch.equal(y1, y2) and torch.equal(y2, y
     assert res["hit"] and res["same"] and res["w_inval"] and res["a_inval"], res
     assert res["grad"] in (True, "n/a"), res
     assert res["hooks"], res
+
+
+def test_module_forward_is_cuda_graph_capturable():
+    """The steady-state module call allocates through torch's graph-aware allocator, never synchronises and never reads
+    device memory on the host: a whole TensorQuantizer.forward (weights and activations, ANT and closed-form kernels)
+    can be captured in a CUDA graph and replayed on new data."""
+    res, _ = run("ant", r'''
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+outs = {}
+for name, mode, bit, is_input, shape in (("w4", "flint", 4, False, (256, 1024)), ("w8", "int", 8, False, (256, 1024)),
+                                          ("a4", "flint", 4, True, (64, 4096))):
+    q = TensorQuantizer(mode=mode, bit=bit, is_signed=not is_input, is_enable=True, is_input=is_input, args=mkargs(mode)).to(dev)
+    if not is_input:
+        q.alpha.data = torch.ones([shape[0], 1], device=dev)
+    q.enable_quantization(name)
+    x = torch.randn(*shape, device=dev).half()
+    if is_input:
+        x = x.abs()
+    with torch.no_grad():
+        q(x)                                           # calibrate outside the graph
+        q(x)
+        static_x = x.clone()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            q(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g):
+            static_y = q(static_x)
+        x2 = (x * 0.7).contiguous()
+        static_x.copy_(x2)
+        g.replay()
+        torch.cuda.synchronize()
+        outs[name] = bool(torch.equal(static_y, q(x2)))
+RESULT.update(outs)
+''', timeout=600)
+    assert res == {"w4": True, "w8": True, "a4": True}, res
