@@ -54,6 +54,7 @@ def _load():
     L.antq_fakequant.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ip, ci, vp]
     L.antq_fakequant_plan.argtypes = [ip, i64, i64, ci, ci, vp, vp, vp]
     L.antq_absmax.argtypes = [vp, vp, i64, i64, ci, vp]
+    L.antq_fakequant_dynamic.argtypes = [vp, vp, vp, ctypes.c_float, i64, i64, ci, vp, ip, ci, vp]
     L.antq_mse_sweep.argtypes = [vp, vp, ci, vp, ci, vp, i64, i64, ci, vp, ci, vp]
     u32p = ctypes.POINTER(ctypes.c_uint32)
     L.antq_encode_p4.argtypes = [vp, vp, vp, ci, i64, i64, ci, vp, ip, ci, vp, vp]
@@ -76,7 +77,7 @@ def _load():
     for name in ("antq_codebook_prepare", "antq_codebook_info_get", "antq_lut_nearest", "antq_fakequant",
                  "antq_fakequant_plan", "antq_absmax", "antq_mse_sweep", "antq_host_create",
                  "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches",
-                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate", "antq_linear_p4"):
+                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate", "antq_linear_p4", "antq_fakequant_dynamic"):
         getattr(L, name).restype = ci
     return L
 

@@ -191,6 +191,33 @@ def fakequant_grouped(x, alpha, cb, group_size, ovp=False, out=None):
     return y.view(x.shape) if out is None else out
 
 
+def fakequant_dynamic(x, cb, group_size, ratio=1.0, return_alpha=False, out=None):
+    """Group-wise DYNAMIC scales in one pass: alpha = max|x| over each `group_size` consecutive elements * ratio, then the
+    fused fake-quant with that alpha (antq_fakequant_dynamic: one HBM read).  Falls back to absmax + fakequant_grouped
+    (two reads) for the shapes / grids the single-pass kernel declines."""
+    _need_cuda(x, "x")
+    if not x.is_contiguous():
+        raise RuntimeError("antq: x must be contiguous")
+    g = int(group_size)
+    if g <= 0 or x.numel() % g:
+        raise ValueError("antq: numel (%d) is not a multiple of the group size (%d)" % (x.numel(), g))
+    rows = x.numel() // g
+    with _maybe_guard(x.device):
+        if out is None:
+            out = torch.empty_like(x)
+        else:
+            _check_out(out, x)
+        alpha = torch.empty(rows, dtype=torch.float32, device=x.device) if return_alpha else None
+        rc = lib.antq_fakequant_dynamic(_ptr(x), _ptr(out), _ptr(alpha), float(ratio), rows, g, _dtype_code(x), cb.ptr,
+                                        cb.info_ref, 0, _stream())
+        if rc == _lib.ENOTSUP:
+            alpha = absmax(x.view(rows, g), True) * float(ratio)
+            fakequant(x.view(rows, g), alpha, cb, True, out=out.view(rows, g))
+        else:
+            check(rc, "antq_fakequant_dynamic")
+    return (out, alpha) if return_alpha else out
+
+
 def fakequant_plan(x, cb, per_row, ovp=False, flags=0):
     rows, cols = _rows_cols(x, per_row)
     fl = flags | (_lib.FLAG_OVP if ovp else 0)

@@ -16,6 +16,8 @@ int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alph
                           int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
 int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
+int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float ratio, long long rows, long long cols, int dtype,
+                           const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
 int antq_launch_flat(const void *x, void *out, int16_t *codes, const float *alpha, int alpha_per_row, long long rows,
                      long long cols, int dtype, const AntqCodebook *cb, bool scale, bool ovp, cudaStream_t st);
 int antq_launch_absmax(const void *x, float *out, long long rows, long long cols, int dtype, cudaStream_t st);
@@ -147,6 +149,18 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
     if (flags & (ANTQ_FLAG_FORCE_ROWS | ANTQ_FLAG_FORCE_PU)) return ANTQ_ENOTSUP;
     // every shape, alignment and grid: the generic kernel (also the only one that emits int16 code indices)
     return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp, st);
+}
+
+int antq_fakequant_dynamic(const void *x, void *out, float *alpha_out, float ratio, int64_t rows, int64_t cols, int dtype,
+                           const void *codebook, const antq_codebook_info *info, int flags, void *stream) {
+    const int es = esize(dtype);
+    if (es == 0 || rows < 0 || cols < 0 || !info) return ANTQ_EINVAL;
+    if (rows == 0 || cols == 0) return 0;
+    if (!x || !out || !codebook) return ANTQ_EINVAL;
+    if ((uintptr_t)x % 16 || (uintptr_t)out % 16) return ANTQ_EALIGN;
+    if (flags & ANTQ_FLAG_OVP) return ANTQ_ENOTSUP;
+    return antq_launch_pu_dynamic(x, out, alpha_out, ratio, rows, cols, dtype, (const AntqCodebook *)codebook, info,
+                                  (cudaStream_t)stream);
 }
 
 int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype, void *stream) {

@@ -457,6 +457,59 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
     }
 }
 
+// ==================================================================================================
+// Dynamic scale groups: alpha = max|x| over the group * ratio, computed in the same pass (ONE read of x).
+// A group of cols = L * VEC elements is held by L adjacent lanes (L a power of two <= 32): local abs-max, xor-shuffle
+// reduction (integer max on the fp32 bit patterns of |x|: NaN-propagating, like torch's abs().max()), then the closed form.
+// ==================================================================================================
+template <typename T, bool UNIFORM>
+__global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const PuParams p, float ratio, float *__restrict__ alpha_out) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    __shared__ float2 tab[UNIFORM ? 1 : 512];
+    __shared__ float x_thr[ANTQ_MAX_GRID], x_lev[ANTQ_MAX_GRID];
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
+    }
+    PuExact X;
+    X.thr = x_thr; X.lev = x_lev; X.nlev = p.cb->n_levels;
+    X.win = (p.cb->flags & ANTQ_CB_WELLSEP) ? p.cb->lim_idx : -1.0f;
+    for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
+    __syncthreads();
+    const PuK K = pu_load_k(p.cb);
+    const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
+    uint4 *xout = reinterpret_cast<uint4 *>(p.out);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned L = p.cols_vec;                                    // lanes per group
+    const unsigned nvec_up = (p.nvec + 31u) & ~31u;                   // every lane of a warp runs the same trip count
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec_up; v += stride) {
+        const bool live = v < p.nvec;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (live) raw = antq_ldg_stream(xin + v);
+        T xv[VEC];
+        *reinterpret_cast<uint4 *>(xv) = raw;
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+            const unsigned b = __float_as_uint(A::to_f32(xv[e])) & 0x7fffffffu;
+            m = b > m ? b : m;
+        }
+        for (unsigned o = 1; o < L; o <<= 1) {
+            const unsigned t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        const float alpha = __fmul_rn(__uint_as_float(m), ratio);     // alpha = absmax * ratio (fp32, like the torch expression)
+        if (!live) continue;
+        if (alpha_out && (v & (L - 1)) == 0) alpha_out[v >> p.cols_shift] = alpha;
+        const PuRow r = pu_row<T>(alpha, p, K, true);
+        bool flag = true;
+        uint4 q = raw;
+        if (r.ok) q = pu_vec<T, UNIFORM>(raw, r, K, tab, flag);
+        antq_stg_stream(xout + v, q);
+        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+    }
+}
+
 template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_pu_stream_kernel<T, UNIFORM>;
     const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kNC * kListMax * 2;
@@ -572,4 +625,45 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     }
 #undef ANTQ_PU_GO
     return ANTQ_EINVAL;
+}
+
+// Dynamic group scales (see antq_pu_dynamic_kernel).  ENOTSUP: grids that are not piecewise uniform, groups that do not fit
+// one warp (more than 32 x 16 bytes) or whose vector count is not a power of two.
+int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float ratio, long long rows, long long cols, int dtype,
+                           const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st) {
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
+    const int vec = 16 / es;
+    const long long n = rows * cols;
+    if (n == 0) return 0;
+    if (!(info->flags & ANTQ_CB_PU) || !(info->flags & ANTQ_CB_WELLSEP) || !(info->flags & ANTQ_CB_STE_EXACT)) return ANTQ_ENOTSUP;
+    if (cols % vec || (n / vec) > 0x7ffffff0LL) return ANTQ_ENOTSUP;
+    const long long cv = cols / vec;
+    if (cv > 32 || (cv & (cv - 1))) return ANTQ_ENOTSUP;
+    PuParams p = {};
+    p.x = x; p.out = out; p.alpha = nullptr; p.cb = cb;
+    p.rows = rows; p.cols = cols;
+    p.nvec = (unsigned)(n / vec);
+    p.cols_vec = (unsigned)cv;
+    int sh = 0;
+    while ((1u << sh) < p.cols_vec) sh++;
+    p.cols_shift = sh;
+    p.alpha_per_row = 1;
+    p.gmax = info->gmax; p.lim = info->lim;
+    const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
+    const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
+    const long long cap = (long long)antq_num_sms() * 8;
+    const int ctas = (int)(want < cap ? want : cap);
+#define ANTQ_PU_GO(T)                                                                                      \
+    do {                                                                                                   \
+        if (uni) antq_pu_dynamic_kernel<T, true><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);     \
+        else antq_pu_dynamic_kernel<T, false><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);        \
+    } while (0)
+    switch (dtype) {
+        case ANTQ_F32: ANTQ_PU_GO(float); break;
+        case ANTQ_F16: ANTQ_PU_GO(__half); break;
+        case ANTQ_BF16: ANTQ_PU_GO(__nv_bfloat16); break;
+        default: return ANTQ_EINVAL;
+    }
+#undef ANTQ_PU_GO
+    return (int)cudaGetLastError();
 }

@@ -121,6 +121,15 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
 int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t cols, int dtype, int flags,
                         const void *x, const void *out, const void *codes);
 
+/* Dynamic group scales in ONE read of x (north star: "group-wise abs-max ... with warp shuffles, encodes and decodes in
+ * registers"): alpha[r] = fl32(max_c |x[r, c]| * ratio), then the fused fake-quant of row r with that alpha -- the
+ * reference's per-channel path (A/antquant/quant_modules.py:473-477 + 535-551) on the [numel / G, G] view, without the
+ * separate abs-max pass.  alpha_out (optional, rows floats) receives the scales.  Piecewise-uniform grids, no OVP, rows
+ * of at most 32 16-byte vectors with a power-of-two vector count (group-8 ... 256 for fp16): otherwise ANTQ_ENOTSUP and
+ * the caller runs antq_absmax + antq_fakequant. */
+int antq_fakequant_dynamic(const void *x, void *out, float *alpha_out, float ratio, int64_t rows, int64_t cols, int dtype,
+                           const void *codebook, const antq_codebook_info *info, int flags, void *stream);
+
 /* out[r] = max_c |x[r, c]| as fp32 (rows = 1: whole tensor). */
 int antq_absmax(const void *x, float *out, int64_t rows, int64_t cols, int dtype, void *stream);
 

@@ -156,3 +156,36 @@ def test_pu_headline_sizes_against_flat(antq):
         y = antq.fakequant(x, a0, cb, False)
         yf = antq.fakequant(x, a0, cb, False, flags=_lib.FLAG_FORCE_FLAT)
         assert torch.equal(y.view(torch.int16), yf.view(torch.int16)), (kind, bit, shape, "per-tensor")
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32", "bf16"])
+@pytest.mark.parametrize("kind,bit,signed", [("flint", 4, True), ("int", 8, True), ("flint", 4, False), ("int", 4, True)])
+def test_dynamic_group_scales_single_pass(antq, kind, bit, signed, dtype):
+    """antq_fakequant_dynamic: alpha = max|x| of each group * ratio computed in the same pass as the fake-quant (one HBM
+    read) == the reference's per-channel path on the [numel / G, G] view with alpha = x.abs().max(1) * ratio."""
+    rng = np.random.default_rng(41 + bit)
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = _cb(antq, grid)
+    n = 1 << 17
+    x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    x[rng.integers(0, n, 40)] *= 30
+    x[1024:1024 + 256] = 0.0                      # dead groups: alpha = 0 -> NaN, as in the reference
+    x[5000] = np.nan
+    if not signed:
+        x = np.abs(x)
+    tdt = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[dtype]
+    xt = torch.from_numpy(x).to(tdt)
+    xd = xt.to(dev())
+    for g in (8, 16, 32, 64, 256, 512):
+        for ratio in (1.0, 0.85):
+            xf = xt.float().numpy().reshape(-1, g)
+            alpha = (np.abs(xf).max(1) * np.float32(ratio)).astype(np.float32)
+            alpha[np.isnan(xf).any(1)] = np.nan
+            ref32 = orc.ant_forward(xf, alpha, grid, per_row=True)
+            ref = torch.from_numpy(ref32).to(tdt)
+            y, a = antq.fakequant_dynamic(xd, cb, g, ratio=ratio, return_alpha=True)
+            a = a.cpu().numpy()
+            assert np.array_equal(np.isnan(a), np.isnan(alpha)) and np.array_equal(a[~np.isnan(a)], alpha[~np.isnan(alpha)]), (g, ratio)
+            yc = y.cpu().reshape(-1, g)
+            same = (yc.view(torch.int16 if tdt != torch.float32 else torch.int32) == ref.view(torch.int16 if tdt != torch.float32 else torch.int32)) | (yc.isnan() & ref.isnan())
+            assert bool(same.all()), (g, ratio, int((~same).sum()))
