@@ -73,14 +73,25 @@ __device__ int antq_pu_analyze(const float *lev, int L, int *ku, AntqCodebook *c
     for (int E = 0; E < 256; E++) {
         int e = E - 127;
         e = e < 0 ? 0 : (e > e_top ? e_top : e);
-        cb->pu_tab[E] = make_float2(__uint_as_float(((unsigned)(150 + ls[e]) << 23) | 0x400000u),   // 1.5 * 2^(23 + ls)
-                                    __uint_as_float((unsigned)(127 + e - 19) << 23));              // 2^(e - 19)
+        // .x = 1.5 * 2^(23 + ls): the rounding magic;  .y = step / 2 - 2^(e - 19): |t - round(t)| at or above it means
+        // "within delta of a midpoint" (|t - round(t)| never exceeds step / 2)
+        const float half_step = __uint_as_float((unsigned)(127 + ls[e] - 1) << 23);
+        const float delta = __uint_as_float((unsigned)(127 + e - 19) << 23);
+        cb->pu_tab[E] = make_float2(__uint_as_float(((unsigned)(150 + ls[e]) << 23) | 0x400000u), __fsub_rn(half_step, delta));
     }
     cb->pu_c = c;
     cb->pu_inv_c = __fdiv_rn(1.0f, c);
     cb->pu_kmin = kmin;
     cb->pu_kmax = kmax;
-    return ANTQ_CB_PU | (uniform ? ANTQ_CB_PU_UNIFORM : 0);
+    // May the clamp be applied to the 16-bit input instead of to t?  The bounds (kmax + 0.4 step) / kx and (kmin - 0.4 step)
+    // / kx (step = that of the octave the end lies in; kmin = 0: the sub-unit region) are rounded toward zero to the
+    // input type: a relative error < 2^-10 (fp16) / 2^-7 (bf16) must keep them beyond the last midpoint.
+    auto oct_of = [&](float k) { int e = 0; while (e < e_top && (float)(2 << e) <= k) e++; return k < 1.0f ? 0 : e; };
+    const float step_hi = (float)(1 << ls[oct_of(kmax)]), step_lo = (float)(1 << ls[oct_of(-kmin)]);
+    int xc = 0;
+    if (kmax <= 400.0f * step_hi && -kmin <= 400.0f * step_lo) xc |= ANTQ_CB_PU_XC16;
+    if (kmax <= 48.0f * step_hi && -kmin <= 48.0f * step_lo) xc |= ANTQ_CB_PU_XCBF;
+    return ANTQ_CB_PU | (uniform ? ANTQ_CB_PU_UNIFORM : 0) | xc;
 }
 
 __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float *__restrict__ grid, int k_normal,

@@ -28,11 +28,13 @@
 
 namespace {
 
-constexpr int kNC = 12;                   // consumer warps per CTA
+#ifndef ANTQ_PU_CONSUMERS
+#define ANTQ_PU_CONSUMERS 16
+#endif
+constexpr int kNC = ANTQ_PU_CONSUMERS;    // consumer warps per CTA
 constexpr int kNS = 2 * kNC;              // two private stages per warp
 constexpr int kChunkMax = 4096;
 constexpr int kThreads = kNC * 32;
-constexpr unsigned kHalfFromMagic = 0x0C400000u;   // bits(1.5 * 2^k) - bits(2^(k - 24))
 constexpr int kListMax = 512;             // per-warp work list of elements to redo exactly (per chunk)
 
 struct PuParams {
@@ -52,16 +54,24 @@ struct PuParams {
 
 struct PuK {                               // the codebook's closed-form constants (AntqCodebook::pu_*)
     float c, inv_c, kmin, kmax;
+    float xc_lo, xc_hi;                    // x-space clamp: (kmin - 0.4 step_top) and (kmax + 0.4 step_top), in units of c
 };
 __device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
     PuK k;
     k.c = cb->pu_c; k.inv_c = cb->pu_inv_c; k.kmin = cb->pu_kmin; k.kmax = cb->pu_kmax;
+    // step of the octave each end of the grid lies in, from that octave's magic constant M = 1.5 * 2^23 * step
+    // (kmin = 0: exponent field 0 -> the sub-unit region's entry)
+    const float step_hi = __fmul_rn(cb->pu_tab[__float_as_uint(k.kmax) >> 23].x, 7.94728597e-08f);           // 1 / (1.5 * 2^23)
+    const float step_lo = __fmul_rn(cb->pu_tab[(__float_as_uint(k.kmin) & 0x7fffffffu) >> 23].x, 7.94728597e-08f);
+    k.xc_hi = __fadd_rn(k.kmax, __fmul_rn(0.4f, step_hi));
+    k.xc_lo = __fsub_rn(k.kmin, __fmul_rn(0.4f, step_lo));
     return k;
 }
 
 struct PuRow {
     float s, kx, xl;
     uint32_t xl2;                     // 16-bit types: xl rounded toward zero, in both halves
+    uint32_t xlo2, xhi2;              // 16-bit types: x-space clamp bounds (rounded toward zero), in both halves
     bool ok;
 };
 
@@ -76,33 +86,36 @@ __device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const Pu
     r.kx = __fmul_rn(rs, K.inv_c);
     r.ok = r.s > 0.0f && r.s < inf && r.kx > 0.0f && r.kx < inf;
     r.xl = __fmul_rn(__fmul_rn(p.lim, r.s), 0.9990234375f);           // conservative exact window in x-space
-    r.xl2 = 0;
+    r.xl2 = 0; r.xlo2 = 0; r.xhi2 = 0;
     if constexpr (sizeof(T) == 2) {
         const uint32_t b = AntqType<T>::bits(AntqType<T>::from_f32_rz(r.xl));
         r.xl2 = b | (b << 16);
+        const float sc = __fmul_rn(r.s, K.c);                          // ~ 1 / kx
+        const uint32_t lo = AntqType<T>::bits(AntqType<T>::from_f32_rz(__fmul_rn(K.xc_lo, sc)));
+        const uint32_t hi = AntqType<T>::bits(AntqType<T>::from_f32_rz(__fmul_rn(K.xc_hi, sc)));
+        r.xlo2 = lo | (lo << 16); r.xhi2 = hi | (hi << 16);
     }
     return r;
 }
 
-// The closed form for one element.  `flag` accumulates "redo me exactly".
-template <bool UNIFORM>
+// The closed form for one element.  `flag` accumulates "redo me exactly".  CLAMP = false: the input was already clamped
+// in x-space (packed min / max on the 16-bit pairs), so t cannot round beyond [kmin, kmax].
+template <bool UNIFORM, bool CLAMP>
 __device__ __forceinline__ float pu_quant(float xf, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
     const float t = __fmul_rn(xf, r.kx);
-    float M, dl;
+    float M, hd;
     if (UNIFORM) {
         M = 12582912.0f;                                              // 1.5 * 2^23: step 1 everywhere
-        dl = __fmul_rn(fabsf(t), 1.9073486328125e-06f);               // |t| 2^-19 (2^-20 at the first midpoint, t = 0.5)
+        hd = __fmaf_rn(fabsf(t), -1.9073486328125e-06f, 0.5f);        // 0.5 - |t| 2^-19
     } else {
         const float2 md = tab[__float_as_uint(t) >> 23];              // sign + exponent index a 512-entry table
-        M = md.x; dl = md.y;
+        M = md.x; hd = md.y;                                          // step / 2 - delta_e
     }
     const float mf = __fsub_rn(__fadd_rn(t, M), M);
-    const float rr = __fsub_rn(t, mf);                                // exact
-    const float h = UNIFORM ? 0.5f : __uint_as_float(__float_as_uint(M) - kHalfFromMagic);
-    const float v = __fsub_rn(fabsf(rr), h);
-    flag |= fabsf(v) <= dl;
-    const float q = __fmul_rn(fminf(fmaxf(mf, K.kmin), K.kmax), K.c);
-    return __fmul_rn(q, r.s);
+    const float rr = __fsub_rn(t, mf);                                // exact; |rr| <= step / 2
+    flag |= fabsf(rr) >= hd;                                          // within delta of a midpoint
+    const float mc = CLAMP ? fminf(fmaxf(mf, K.kmin), K.kmax) : mf;
+    return __fmul_rn(__fmul_rn(mc, K.c), r.s);
 }
 
 // Exact thresholds and levels of the codebook, staged in shared memory for the redo path (the rank search is 3-8
@@ -136,6 +149,8 @@ template <> struct PuPack<__nv_bfloat16> {
     typedef __nv_bfloat162 v2;
     __device__ static __forceinline__ v2 from_u32(uint32_t u) { return *reinterpret_cast<v2 *>(&u); }
 };
+
+template <typename V> __device__ __forceinline__ uint32_t antq_pu_u32(const V &v) { return *reinterpret_cast<const uint32_t *>(&v); }
 
 template <typename T> struct PuIO;
 template <> struct PuIO<float> {
@@ -179,25 +194,36 @@ template <> struct PuIO<__nv_bfloat16> {
 };
 
 // One 16-byte vector through the closed form; `flag` = some element needs the exact redo.
-template <typename T, bool UNIFORM>
+// XC (16-bit types): clamp the INPUT pairs with two packed min / max instead of every t with two FMNMX.
+template <typename T, bool UNIFORM, bool XC>
 __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
     constexpr int VEC = PuIO<T>::VEC;
     float f[VEC], o[VEC];
-    PuIO<T>::unpack(raw, f);
     bool fl = false;
+    if constexpr (sizeof(T) == 2) {
+        typedef typename PuPack<T>::v2 v2;
+        // one packed NaN-propagating max of |x| per vector against the exact window
+        const v2 a = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.x)), __habs2(PuPack<T>::from_u32(raw.y)));
+        const v2 b = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.z)), __habs2(PuPack<T>::from_u32(raw.w)));
+        fl |= __hle2_mask(__hmax2_nan(a, b), PuPack<T>::from_u32(r.xl2)) != 0xffffffffu;
+        if constexpr (XC) {
+            const v2 lo = PuPack<T>::from_u32(r.xlo2), hi = PuPack<T>::from_u32(r.xhi2);
+            uint4 c;
+            c.x = antq_pu_u32(__hmin2(__hmax2(PuPack<T>::from_u32(raw.x), lo), hi));
+            c.y = antq_pu_u32(__hmin2(__hmax2(PuPack<T>::from_u32(raw.y), lo), hi));
+            c.z = antq_pu_u32(__hmin2(__hmax2(PuPack<T>::from_u32(raw.z), lo), hi));
+            c.w = antq_pu_u32(__hmin2(__hmax2(PuPack<T>::from_u32(raw.w), lo), hi));
+            PuIO<T>::unpack(c, f);
+        } else {
+            PuIO<T>::unpack(raw, f);
+        }
+    } else {
+        PuIO<T>::unpack(raw, f);
+    }
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
-        o[e] = pu_quant<UNIFORM>(f[e], r, K, tab, fl);
+        o[e] = pu_quant<UNIFORM, !(XC && sizeof(T) == 2)>(f[e], r, K, tab, fl);
         if (sizeof(T) == 4) fl |= !(fabsf(f[e]) <= r.xl);             // outside the exact window, NaN, Inf
-    }
-    if (sizeof(T) == 2) {
-        // 16-bit types: one packed NaN-propagating max of |x| per vector against the window
-        if constexpr (sizeof(T) == 2) {
-            typedef typename PuPack<T>::v2 v2;
-            const v2 a = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.x)), __habs2(PuPack<T>::from_u32(raw.y)));
-            const v2 b = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.z)), __habs2(PuPack<T>::from_u32(raw.w)));
-            fl |= __hle2_mask(__hmax2_nan(a, b), PuPack<T>::from_u32(r.xl2)) != 0xffffffffu;
-        }
     }
     flag = fl;
     return PuIO<T>::pack(o);
@@ -214,7 +240,7 @@ __device__ __forceinline__ unsigned pu_vec_mask(const uint4 raw, const PuRow &r,
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
         bool fl = false;
-        (void)pu_quant<UNIFORM>(f[e], r, K, tab, fl);
+        (void)pu_quant<UNIFORM, true>(f[e], r, K, tab, fl);
         fl |= !(fabsf(f[e]) <= r.xl);
         m |= (fl ? 1u : 0u) << e;
     }
@@ -246,7 +272,7 @@ __device__ __forceinline__ void pu_mbar_arrive(uint64_t *bar) {
 // ==================================================================================================
 // Long rows / per-tensor: persistent CTAs, TMA-staged chunks.
 // ==================================================================================================
-template <typename T, bool UNIFORM>
+template <typename T, bool UNIFORM, bool XC>
 __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
@@ -348,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             for (int v = lane; v + 32 < nvec; v += 64, j += 2) {
                 const uint4 r0 = sp[0], r1 = sp[32];
                 bool f0, f1;
-                const uint4 q0 = pu_vec<T, UNIFORM>(r0, r, K, tab, f0);
-                const uint4 q1 = pu_vec<T, UNIFORM>(r1, r, K, tab, f1);
+                const uint4 q0 = pu_vec<T, UNIFORM, XC>(r0, r, K, tab, f0);
+                const uint4 q1 = pu_vec<T, UNIFORM, XC>(r1, r, K, tab, f1);
                 antq_stg_stream(op, q0);
                 antq_stg_stream(op + 32, q1);
                 redo |= (f0 ? 1u : 0u) << j;
@@ -358,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             }
             if (j * 32 + lane < nvec) {
                 bool f0;
-                const uint4 q0 = pu_vec<T, UNIFORM>(*sp, r, K, tab, f0);
+                const uint4 q0 = pu_vec<T, UNIFORM, XC>(*sp, r, K, tab, f0);
                 antq_stg_stream(op, q0);
                 redo |= (f0 ? 1u : 0u) << j;
             }
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
 // ==================================================================================================
 constexpr int kShortThreads = 256;
 
-template <typename T, bool UNIFORM>
+template <typename T, bool UNIFORM, bool XC>
 __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const PuParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
@@ -451,7 +477,7 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
         const PuRow r = pu_row<T>(__ldg(p.alpha + row), p, K, true);
         bool flag = true;
         uint4 q = raw;
-        if (r.ok) q = pu_vec<T, UNIFORM>(raw, r, K, tab, flag);
+        if (r.ok) q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, flag);
         antq_stg_stream(xout + v, q);
         if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
     }
@@ -462,7 +488,7 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
 // A group of cols = L * VEC elements is held by L adjacent lanes (L a power of two <= 32): local abs-max, xor-shuffle
 // reduction (integer max on the fp32 bit patterns of |x|: NaN-propagating, like torch's abs().max()), then the closed form.
 // ==================================================================================================
-template <typename T, bool UNIFORM>
+template <typename T, bool UNIFORM, bool XC>
 __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const PuParams p, float ratio, float *__restrict__ alpha_out) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
@@ -504,14 +530,14 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const
         const PuRow r = pu_row<T>(alpha, p, K, true);
         bool flag = true;
         uint4 q = raw;
-        if (r.ok) q = pu_vec<T, UNIFORM>(raw, r, K, tab, flag);
+        if (r.ok) q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, flag);
         antq_stg_stream(xout + v, q);
         if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
     }
 }
 
-template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
-    auto kernel = antq_pu_stream_kernel<T, UNIFORM>;
+template <typename T, bool UNIFORM, bool XC> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
+    auto kernel = antq_pu_stream_kernel<T, UNIFORM, XC>;
     const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kNC * kListMax * 2;
     static unsigned long long configured = 0ull;                     // one bit per device ordinal
     int dev = 0;
@@ -537,10 +563,10 @@ template <typename T, bool UNIFORM> int launch_stream(const PuParams &p, int cta
     return (int)e;
 }
 
-template <typename T, bool UNIFORM> int launch_short(const PuParams &p, cudaStream_t st) {
+template <typename T, bool UNIFORM, bool XC> int launch_short(const PuParams &p, cudaStream_t st) {
     const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
     const long long cap = (long long)antq_num_sms() * 8;
-    antq_pu_short_kernel<T, UNIFORM><<<(int)(want < cap ? want : cap), kShortThreads, 0, st>>>(p);
+    antq_pu_short_kernel<T, UNIFORM, XC><<<(int)(want < cap ? want : cap), kShortThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -586,11 +612,12 @@ int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alph
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
     p.chunks_rem = p.total_chunks % (unsigned)ctas;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
-#define ANTQ_PU_GO(T) (uni ? launch_stream<T, true>(p, ctas, st) : launch_stream<T, false>(p, ctas, st))
+    const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
+#define ANTQ_PU_GO(T, X) (uni ? launch_stream<T, true, X>(p, ctas, st) : launch_stream<T, false, X>(p, ctas, st))
     switch (dtype) {
-        case ANTQ_F32: return ANTQ_PU_GO(float);
-        case ANTQ_F16: return ANTQ_PU_GO(__half);
-        case ANTQ_BF16: return ANTQ_PU_GO(__nv_bfloat16);
+        case ANTQ_F32: return ANTQ_PU_GO(float, false);
+        case ANTQ_F16: return xc ? ANTQ_PU_GO(__half, true) : ANTQ_PU_GO(__half, false);
+        case ANTQ_BF16: return xc ? ANTQ_PU_GO(__nv_bfloat16, true) : ANTQ_PU_GO(__nv_bfloat16, false);
     }
 #undef ANTQ_PU_GO
     return ANTQ_EINVAL;
@@ -617,11 +644,12 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     p.alpha_per_row = alpha_per_row;
     p.gmax = info->gmax; p.lim = info->lim;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
-#define ANTQ_PU_GO(T) (uni ? launch_short<T, true>(p, st) : launch_short<T, false>(p, st))
+    const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
+#define ANTQ_PU_GO(T, X) (uni ? launch_short<T, true, X>(p, st) : launch_short<T, false, X>(p, st))
     switch (dtype) {
-        case ANTQ_F32: return ANTQ_PU_GO(float);
-        case ANTQ_F16: return ANTQ_PU_GO(__half);
-        case ANTQ_BF16: return ANTQ_PU_GO(__nv_bfloat16);
+        case ANTQ_F32: return ANTQ_PU_GO(float, false);
+        case ANTQ_F16: return xc ? ANTQ_PU_GO(__half, true) : ANTQ_PU_GO(__half, false);
+        case ANTQ_BF16: return xc ? ANTQ_PU_GO(__nv_bfloat16, true) : ANTQ_PU_GO(__nv_bfloat16, false);
     }
 #undef ANTQ_PU_GO
     return ANTQ_EINVAL;
@@ -653,15 +681,16 @@ int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float rat
     const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
     const long long cap = (long long)antq_num_sms() * 8;
     const int ctas = (int)(want < cap ? want : cap);
-#define ANTQ_PU_GO(T)                                                                                      \
-    do {                                                                                                   \
-        if (uni) antq_pu_dynamic_kernel<T, true><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);     \
-        else antq_pu_dynamic_kernel<T, false><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);        \
+    const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
+#define ANTQ_PU_GO(T, X)                                                                                      \
+    do {                                                                                                      \
+        if (uni) antq_pu_dynamic_kernel<T, true, X><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);     \
+        else antq_pu_dynamic_kernel<T, false, X><<<ctas, kShortThreads, 0, st>>>(p, ratio, alpha_out);        \
     } while (0)
     switch (dtype) {
-        case ANTQ_F32: ANTQ_PU_GO(float); break;
-        case ANTQ_F16: ANTQ_PU_GO(__half); break;
-        case ANTQ_BF16: ANTQ_PU_GO(__nv_bfloat16); break;
+        case ANTQ_F32: ANTQ_PU_GO(float, false); break;
+        case ANTQ_F16: if (xc) ANTQ_PU_GO(__half, true); else ANTQ_PU_GO(__half, false); break;
+        case ANTQ_BF16: if (xc) ANTQ_PU_GO(__nv_bfloat16, true); else ANTQ_PU_GO(__nv_bfloat16, false); break;
         default: return ANTQ_EINVAL;
     }
 #undef ANTQ_PU_GO

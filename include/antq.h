@@ -104,6 +104,9 @@ int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, 
 #define ANTQ_CB_PU       32   /* piecewise uniform: levels are fl32(k * c), k integer, power-of-two step per octave
                                  (int / flint / pot / float of every width): the closed-form kernels apply */
 #define ANTQ_CB_PU_UNIFORM 64 /* PU with one step for every octave (int-k) */
+#define ANTQ_CB_PU_XC16  128  /* PU: the clamp to [kmin, kmax] may be done on the fp16 INPUT (packed min / max): the largest
+                                 level is far enough from its lower midpoint for an fp16-rounded bound */
+#define ANTQ_CB_PU_XCBF  256  /* the same for bf16 inputs */
 
 /* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
  * `info` (host pointer, may be NULL) lets the call pick the row-table kernel

@@ -68,28 +68,51 @@ def analyze(grid):
         magic[E] = f32(1.5 * 2.0 ** (23 + ls[e]))
         delta[E] = f32(2.0 ** (e - 19))
     uniform = all(v == 0 for v in ls)
+    # step of the octave each END of the grid lies in (kmin = 0: the sub-unit region, octave 0)
+    oct_of = lambda k: 0 if k < 1 else min(int(np.floor(np.log2(k))), e_top)
+    step_hi = f32(2.0 ** ls[oct_of(float(kmax))])
+    step_lo = f32(2.0 ** ls[oct_of(-float(kmin))])
+    ok = lambda lim: float(kmax) <= lim * float(step_hi) and -float(kmin) <= lim * float(step_lo)
     return dict(c=f32(c), inv_c=f32(f32(1) / c), kmin=f32(kmin), kmax=f32(kmax), magic=magic, delta=delta,
-                e_top=e_top, ls=ls, uniform=uniform)
+                e_top=e_top, ls=ls, uniform=uniform,
+                xc_lo=f32(f32(kmin) - f32(f32(0.4) * step_lo)), xc_hi=f32(f32(kmax) + f32(f32(0.4) * step_hi)),
+                xc16=ok(400.0), xcbf=ok(48.0))
 
 
-def forward(x, s, pu, lim, exact, out_dtype):
+def _rz16(v):
+    """fp32 -> fp16 rounded toward zero."""
+    h = np.float16(v)
+    if abs(float(h)) > abs(float(v)):
+        h = np.nextafter(h, np.float16(0))
+    return h
+
+
+def forward(x, s, pu, lim, exact, out_dtype, xclamp=False):
     """x: array of out_dtype; s: fp32 scale (alpha / max(grid)); lim: the codebook's exact window in d-space.
-    `exact(xs)` is the literal reference arithmetic for the flagged elements.  Returns (out, flagged)."""
+    `exact(xs)` is the literal reference arithmetic for the flagged elements.  Returns (out, flagged).
+    xclamp (fp16 inputs, grids with pu["xc16"]): the clamp to [kmin, kmax] is applied to the INPUT with bounds rounded
+    toward zero to fp16, as the kernel does with two packed min / max per pair, and t is not clamped afterwards."""
     s = f32(s)
     xf = x.astype(f32)
     with np.errstate(all="ignore"):
         rs = f32(1) / s
         kx = f32(rs * pu["inv_c"])
-        t = (xf * kx).astype(f32)
+        xq = xf
+        if xclamp:
+            sc = f32(s * pu["c"])
+            lo, hi = _rz16(f32(pu["xc_lo"] * sc)), _rz16(f32(pu["xc_hi"] * sc))
+            xh = x.astype(np.float16)
+            xh = np.where(np.isnan(xh), lo, np.maximum(xh, lo))          # hmax2 / hmin2 return the non-NaN operand
+            xq = np.minimum(xh, hi).astype(f32)
+        t = (xq * kx).astype(f32)
         E = (_bits(t) >> 23) & 0xff
         M = pu["magic"][E]
         dl = pu["delta"][E]
         mf = ((t + M).astype(f32) - M).astype(f32)
         r = (t - mf).astype(f32)
         h = (_bits(M) - np.uint32((24 << 23) | 0x400000)).view(f32)
-        v = (np.abs(r) - h).astype(f32)
-        near = np.abs(v) <= dl
-        mfc = np.minimum(np.maximum(mf, pu["kmin"]), pu["kmax"]).astype(f32)
+        near = np.abs(r) >= (h - dl).astype(f32)                  # |r| <= h always: "within delta of a midpoint"
+        mfc = mf if xclamp else np.minimum(np.maximum(mf, pu["kmin"]), pu["kmax"]).astype(f32)
         q = (mfc * pu["c"]).astype(f32)
         o = (q * s).astype(f32)
         xl = f32(f32(f32(lim) * s) * f32(0.9990234375))

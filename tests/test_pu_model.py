@@ -36,6 +36,8 @@ def test_analysis_accepts_and_rejects():
     for kind, bit, signed in PU_GRIDS:
         assert pm.analyze(orc.ant_grid(kind, bit, signed)) is not None, (kind, bit, signed)
     assert pm.analyze(orc.ant_grid("int", 8, True))["uniform"]
+    assert pm.analyze(orc.ant_grid("int", 8, False))["xc16"] and not pm.analyze(orc.ant_grid("int", 8, False))["xcbf"]
+    assert pm.analyze(orc.ant_grid("flint", 4, True))["xcbf"]
     assert not pm.analyze(orc.ant_grid("flint", 4, True))["uniform"]
     assert pm.analyze(orc.ant_grid("apot", 4, False)) is None          # 8, 9, 12 in one octave
     # OliVe int + abfloat: 32 itself is missing from the outliers' first octave
@@ -62,6 +64,10 @@ def test_fp16_exhaustive(kind, bit, signed):
         ref = orc.ant_forward(ALL_F16, alpha, grid, per_row=False)
         same = (got.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got) & np.isnan(ref))
         assert same.all(), (kind, bit, signed, s, ALL_F16[~same][:5], got[~same][:5], ref[~same][:5])
+        if pu["xc16"]:                                         # the x-space clamp variant the fp16 kernels take
+            got2, _ = pm.forward(ALL_F16, s_eff, pu, lim_of(cb), exact, np.float16, xclamp=True)
+            same = (got2.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got2) & np.isnan(ref))
+            assert same.all(), ("xclamp", kind, bit, signed, s, ALL_F16[~same][:5], got2[~same][:5], ref[~same][:5])
         inwin = np.abs(ALL_F16.astype(f32)) <= f32(lim_of(cb) * s_eff) * f32(0.99)
         flagged += (fl & inwin).sum() / max(inwin.sum(), 1)
     assert flagged / len(scales(gmax, 6 if bit >= 7 else 10)) < 0.02          # the closed form is what runs
