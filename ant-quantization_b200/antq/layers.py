@@ -14,6 +14,11 @@ import torch.nn.functional as F
 
 
 CACHE_WEIGHTS = os.environ.get("ANTQ_CACHE_WEIGHTS", "1") != "0"
+# "codes": keep the cached weight as packed 4-bit codes + alpha (0.5 byte per element instead of 2 / 4) and decode it on
+# every forward (antq_decode_p4: bit-identical values, one cheap pass) -- for models whose fake-quantized fp copy does not
+# fit next to the original.  Applies where antq_encode_p4 does (grids of <= 16 entries, even rows) and reproduces every
+# value; other layers keep the fp tensor.
+CACHE_FORMAT = os.environ.get("ANTQ_CACHE_FORMAT", "tensor")
 # Opt-in: eval-mode LinearQuantizer layers with a 4-bit weight and fp16 / bf16 activations keep the
 # weight as packed 4-bit codes + one alpha per output channel and run  y = x_q . dequant(W)^T + b  in ONE tcgen05 kernel
 # (antq_linear_p4) instead of fake-quantizing the weight to fp16 and calling cuBLAS.  Numerically this is F.linear on
@@ -72,6 +77,19 @@ def make_layers(TensorQuantizer):
             self.invalidate_weight_cache()
             return super()._load_from_state_dict(*a, **kw)
 
+        def _encode_for_cache(self, weight_q):
+            from . import ops
+            q, w = self.quant_weight, self.weight
+            cb = q._codebook(w.device)
+            n_out = cb.info.n_entries - cb.info.n_normal
+            cols = w.numel() // w.shape[0]
+            if not q.is_perchannel or cols % 2 or (cb.info.n_normal > 15 or n_out > 15 if q._ovp else cb.info.n_entries > 16):
+                return None
+            codes, bad = ops.encode_p4(w.detach().contiguous(), q.alpha, cb, True, ovp=q._ovp)
+            if int(bad.item()) != 0:                         # some value would not be reproduced: keep the fp tensor
+                return None
+            return (codes, q.alpha.detach().reshape(-1).float().contiguous(), cb, q._ovp)
+
         def _weight_key(self):
             q, w = self.quant_weight, self.weight
             if not CACHE_WEIGHTS or self.training or not q._is_inited():
@@ -88,11 +106,17 @@ def make_layers(TensorQuantizer):
             key = self._weight_key()
             if key is not None and key == getattr(self, "_wq_key", None):
                 weight = self._wq_val
+                if isinstance(weight, tuple):                # (codes, alpha, codebook, ovp): decode, bit-identical
+                    from . import ops
+                    weight = ops.decode_p4(weight[0], weight[1], weight[2], self.weight.shape, self.weight.dtype, True,
+                                           ovp=weight[3])
             else:
                 weight = self.quant_weight(self.weight, input)
                 key = self._weight_key()                     # the first call calibrates: take the key afterwards
                 if key is not None and weight is not self.weight:
                     self._wq_key, self._wq_val = key, weight.detach()
+                    if CACHE_FORMAT == "codes":
+                        self._wq_val = self._encode_for_cache(weight) or self._wq_val
                 else:
                     self._wq_key = self._wq_val = None
             input = self.quant_input(input, self.weight)

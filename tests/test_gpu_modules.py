@@ -284,3 +284,36 @@ for name, mode, bit, is_input, shape in (("w4", "flint", 4, False, (256, 1024)),
 RESULT.update(outs)
 ''', timeout=600)
     assert res == {"w4": True, "w8": True, "a4": True}, res
+
+
+@pytest.mark.parametrize("tree", ["ant", "olive"])
+def test_weight_cache_as_packed_codes(tree):
+    """antq.layers.CACHE_FORMAT = "codes": the eval-mode weight cache holds 0.5 byte per element + alpha and decodes on
+    every forward -- outputs bit-identical to the fp-tensor cache and to no cache at all (conv and linear, OliVe pairs)."""
+    res, _ = run(tree, r'''
+import antq.layers as L
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+net = nn.Sequential(nn.Conv2d(8, 16, 3, padding=1), nn.ReLU(), nn.Flatten(), nn.Linear(16 * 6 * 6, 64)).to(dev).half()
+set_quantizer(mkargs("ant-int-flint", w_up=150, a_up=150))
+q = quantize_model(net).to(dev).eval()
+enable_quantization(q)
+x = torch.randn(4, 8, 6, 6, device=dev).half()
+with torch.no_grad():
+    q(x)
+    L.CACHE_WEIGHTS = False
+    y_ref = q(x)
+    L.CACHE_WEIGHTS = True
+    y_tensor = q(x); y_tensor = q(x)
+    L.CACHE_FORMAT = "codes"
+    for m in q.modules():
+        if hasattr(m, "invalidate_weight_cache"): m.invalidate_weight_cache()
+    y_codes = q(x); y_codes2 = q(x)
+    kinds = [type(m._wq_val).__name__ for m in q.modules() if hasattr(m, "_wq_val")]
+    nbytes = [m._wq_val[0].numel() for m in q.modules() if hasattr(m, "_wq_val") and isinstance(m._wq_val, tuple)]
+    L.CACHE_FORMAT = "tensor"
+RESULT.update(same=bool(torch.equal(y_ref, y_tensor) and torch.equal(y_ref, y_codes) and torch.equal(y_codes, y_codes2)),
+              kinds=kinds, nbytes=nbytes)
+''', timeout=600)
+    assert res["same"], res
+    assert res["kinds"] == ["tuple", "tuple"] and res["nbytes"] == [16 * 8 * 9 // 2, 64 * 16 * 36 // 2], res

@@ -62,6 +62,9 @@ def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20):
         if gran == "tensor":
             v, per_row = x, False
             al = x.float().abs().max().reshape(1) * 0.9
+        elif gran.startswith("dyn"):                                  # dynamic group scales: abs-max inside the kernel
+            v, per_row = x.view(-1, int(gran[3:])), True
+            al = torch.zeros(1, device=dev)
         else:
             gsz = n if gran == "row" else int(gran[1:])
             v, per_row = x.view(-1, gsz), True
@@ -70,10 +73,15 @@ def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20):
             al = torch.full_like(al, float(3 * x.float().std()))
         xs.append(v); als.append(al.contiguous()); outs.append(torch.empty_like(v))
     plan = antq.fakequant_plan(xs[0], cb, per_row, ovp=olive, flags=flags)
+    if gran.startswith("dyn"):
+        plan = "dynamic (abs-max + fake-quant, one read)"
 
     def step():
         for i in range(nb):
-            antq.fakequant(xs[i], als[i], cb, per_row, ovp=olive, out=outs[i], flags=flags)
+            if gran.startswith("dyn"):
+                antq.fakequant_dynamic(xs[i].view(-1), cb, int(gran[3:]), ratio=0.9, out=outs[i].view(-1))
+            else:
+                antq.fakequant(xs[i], als[i], cb, per_row, ovp=olive, out=outs[i], flags=flags)
     us = time_graph(step, reps) / nb
     pk, src = peak()
     gbs = n * n * es * 2 / us / 1e3
@@ -115,6 +123,10 @@ def main():
             for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False), ("flint", 4, True, True)):
                 for gr in ("row", "tensor", "g32"):
                     emit(case(n, *t, gr, "f16", reps=10 if n >= 8192 else 20))
+        # dynamic group scales (single read) next to precomputed ones
+        for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False)):
+            for gr in ("dyn8", "dyn32", "dyn128"):
+                emit(case(4096, *t, gr, "f16"))
         # dtypes
         for dt in ("f32", "bf16"):
             for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False)):
