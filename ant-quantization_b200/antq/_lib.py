@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_PKG, "csrc", "libantq%s.so" % os.environ.get("ANTQ_LIB_S
 
 F32, F16, BF16 = 0, 1, 2
 FLAG_OVP, FLAG_FORCE_FLAT, FLAG_FORCE_ROWS, FLAG_FORCE_PU, FLAG_NO_PU = 1, 2, 4, 8, 16
-CB_WELLSEP, CB_STE_EXACT, CB_SYMMETRIC, CB_OVP_OK, CB_SYMX, CB_PU, CB_PU_UNIFORM, CB_PU_XC16, CB_PU_XCBF = 1, 2, 4, 8, 16, 32, 64, 128, 256
+CB_WELLSEP, CB_STE_EXACT, CB_SYMMETRIC, CB_OVP_OK, CB_SYMX, CB_PU, CB_PU_UNIFORM, CB_PU_XC16, CB_PU_XCBF, CB_PU_E4M3 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 EINVAL, ENOTSUP, EALIGN = -1, -2, -3
 MAX_GRID = 512
 CODE_NONE = -1
@@ -67,6 +67,8 @@ def _load():
     L.antq_calibrate.argtypes = [vp, i64, i64, ci, ci, vp, vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ip), ctypes.POINTER(ci),
                                  ci, vp, vp, vp, vp, sz, vp]
     L.antq_linear_p4.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, vp, ip, ci, vp]
+    L.antq_levels_e4m3.argtypes = [vp, vp, vp, i64, ci, vp, ip, vp]
+    L.antq_linear_p4_fp8.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, i64, i64, i64, ci, vp, ip, ci, vp]
     L.antq_host_create.argtypes = [ctypes.POINTER(vp), ci, sz, ci]
     L.antq_host_destroy.argtypes = [vp]
     L.antq_host_destroy.restype = None
@@ -77,7 +79,7 @@ def _load():
     for name in ("antq_codebook_prepare", "antq_codebook_info_get", "antq_lut_nearest", "antq_fakequant",
                  "antq_fakequant_plan", "antq_absmax", "antq_mse_sweep", "antq_host_create",
                  "antq_host_fakequant", "antq_host_fakequant_async", "antq_host_synchronize", "antq_host_last_launches",
-                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate", "antq_linear_p4", "antq_fakequant_dynamic"):
+                 "antq_encode_p4", "antq_decode_p4", "antq_fakequant_backward", "antq_calibrate", "antq_linear_p4", "antq_fakequant_dynamic", "antq_levels_e4m3", "antq_linear_p4_fp8"):
         getattr(L, name).restype = ci
     return L
 

@@ -25,6 +25,10 @@ CACHE_FORMAT = os.environ.get("ANTQ_CACHE_FORMAT", "tensor")
 # the fake-quantized operands up to fp32 accumulation order (tests/test_gpu_gemm.py); off by default because the
 # reference's F.linear rounds differently in the last bit.
 FUSED_LINEAR = os.environ.get("ANTQ_FUSED_LINEAR", "0") == "1"
+# With FUSED_FP8 (default on when FUSED_LINEAR is), W4A4 layers whose two grids are exact in FP8 e4m3 (every 4-bit int /
+# flint / pot / float grid) feed LEVELS to the FP8 tensor cores (tcgen05.mma kind::f8f6f4, twice the 16-bit rate): the
+# integer products are exact in fp32 and both scales are applied in the epilogue.
+FUSED_FP8 = os.environ.get("ANTQ_FUSED_FP8", "1") == "1"
 FUSED_MIN_ROWS = int(os.environ.get("ANTQ_FUSED_MIN_ROWS", "256"))
 
 
@@ -185,8 +189,13 @@ def make_layers(TensorQuantizer):
                     and not (torch.is_grad_enabled() and input.requires_grad):
                 pack = self._weight_codes(input)
                 if pack is not None:
-                    from . import ops
+                    from . import ops, _lib
                     xq = self.quant_input(input, self.weight)
+                    qi = self.quant_input
+                    if FUSED_FP8 and xq is not input and not qi.is_perchannel and not qi._ovp and input.shape[-1] % 128 == 0:
+                        xcb = qi._codebook(input.device)
+                        if (xcb.info.flags & _lib.CB_PU_E4M3) and (pack[2].info.flags & _lib.CB_PU_E4M3):
+                            return ops.linear_p4_fp8(xq, qi.alpha, xcb, pack[0], pack[1], pack[2], self.out_features, self.bias)
                     return ops.linear_p4(xq, pack[0], pack[1], pack[2], self.out_features, self.bias)
             input, weight = self._quantized(input)
             return F.linear(input, weight, self.bias)

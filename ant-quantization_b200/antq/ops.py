@@ -356,6 +356,32 @@ def linear_p4(x, codes, alpha, cb, out_features, bias=None):
     return y.view(*x.shape[:-1], N)
 
 
+def linear_p4_fp8(x_q, x_alpha, x_cb, codes, alpha, cb, out_features, bias=None):
+    """W4A4 on the FP8 tensor cores (antq_levels_e4m3 + antq_linear_p4_fp8): x_q is the fake-quantized activation
+    (per-tensor alpha `x_alpha`, codebook `x_cb`); both operands travel as exact e4m3 levels, the scales are applied in the
+    epilogue.  Needs ANTQ_CB_PU_E4M3 on both codebooks (every 4-bit int / flint / pot / float grid), K % 128 == 0,
+    N % 256 == 0; raises otherwise."""
+    _need_cuda(x_q, "x_q")
+    K = x_q.shape[-1]
+    x2 = x_q.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, N = x2.shape[0], int(out_features)
+    with _maybe_guard(x_q.device):
+        xa = _alpha_arg(x_alpha, 1, False, x_q.device)
+        a = _alpha_arg(alpha, N, True, x_q.device)
+        b = None
+        if bias is not None:
+            b = bias if (bias.dtype is x_q.dtype and bias.is_contiguous()) else bias.detach().to(x_q.dtype).contiguous()
+        lev = torch.empty((M, K), dtype=torch.uint8, device=x_q.device)
+        check(lib.antq_levels_e4m3(_ptr(x2), _ptr(lev), _ptr(xa), M * K, _dtype_code(x2), x_cb.ptr, x_cb.info_ref, _stream()),
+              "antq_levels_e4m3")
+        y = torch.empty((M, N), dtype=x_q.dtype, device=x_q.device)
+        check(lib.antq_linear_p4_fp8(_ptr(lev), _ptr(xa), x_cb.ptr, x_cb.info_ref, _ptr(codes), _ptr(a), _ptr(b), _ptr(y),
+                                     M, N, K, _dtype_code(x2), cb.ptr, cb.info_ref, 0, _stream()), "antq_linear_p4_fp8")
+    return y.view(*x_q.shape[:-1], N)
+
+
 class HostPipeline:
     """antq_host_*: fake-quant of HOST buffers (H2D, kernel, D2H pipelined in chunks)."""
 

@@ -48,6 +48,8 @@ struct GemmParams {
     const void *bias;                 // [N] (operand type) or NULL
     void *y;                          // [M, N]
     const AntqCodebook *cb;
+    const float *x_alpha;             // FP8 mode: the activation quantizer's per-tensor alpha ...
+    const AntqCodebook *x_cb;         // ... and its codebook (unit of the e4m3 levels = alpha / max(grid) * pu_c)
     int M, N, K;
     int m_tiles, n_tiles;
 };
@@ -85,15 +87,27 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool FP8>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (FP8) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
@@ -142,7 +156,25 @@ __device__ __forceinline__ void lut4(uint32_t c, const uint32_t (&lo)[4], const 
     out23 = __byte_perm(l, h, 0x7362u);
 }
 
-template <typename T>
+// The same for ONE byte per code (e4m3 operands): four codes -> four bytes.
+__device__ __forceinline__ uint32_t lut4_b(uint32_t c, const uint32_t (&tb)[4]) {
+    const uint32_t sel = c & 0x7777u;
+    const uint32_t pick = 0x3210u | ((c & 0x8888u) >> 1);
+    return __byte_perm(__byte_perm(tb[0], tb[1], sel), __byte_perm(tb[2], tb[3], sel), pick);
+}
+
+// float -> e4m3 bits (round to nearest even, saturating): only used on values the codebook analysis proved exact
+__device__ __forceinline__ uint32_t e4m3_bits(float v) {
+    unsigned short r;
+    asm("{ .reg .b16 t; cvt.rn.satfinite.e4m3x2.f32 t, %1, %2; mov.b16 %0, t; }" : "=h"(r) : "f"(0.0f), "f"(v));
+    return (uint32_t)(r & 0xffu);
+}
+
+// FP8 = false: x is T (fp16 / bf16), W decoded to T, tcgen05.mma kind::f16, BK = 64 elements.
+// FP8 = true : x is e4m3 LEVELS (one byte per element, antq_levels_e4m3), W decoded to e4m3 levels, kind::f8f6f4 at twice
+//              the tensor rate, BK = 128 elements; the products are small integers, exact in the fp32 accumulator;
+//              both scales are applied in the epilogue.  Byte geometry (128-byte rows, 32 bytes per MMA k-step) is the same.
+template <typename T, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char gsm_raw[];
     // the 128-byte swizzle pattern is a function of the shared-memory ADDRESS: tiles must start 1024-byte aligned
@@ -158,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
     float *s_bias = s_scale + 2 * BN;                                      // [2][BN] (only buffer 0 is used with one accumulator)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = p.K / BK;
+    constexpr int BKE = FP8 ? 2 * BK : BK;                                  // elements of K per stage (128 bytes per row)
+    const int num_kb = p.K / BKE;
     const int num_tiles = p.m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
@@ -186,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(empty + stage, phase ^ 1u);
                     mbar_expect_tx(full + stage, kStageA);
-                    tma_load_2d(smem_a + stage * kStageA, &tmap_x, full + stage, kb * BK, m_blk * BM);
+                    tma_load_2d(smem_a + stage * kStageA, &tmap_x, full + stage, kb * BKE, m_blk * BM);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -195,7 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A / B format << 7 / << 10, K-major both, N >> 3 << 17, M >> 4 << 24
-            const uint32_t idesc = (1u << 4) | (Op16<T>::kFormat << 7) | (Op16<T>::kFormat << 10) | ((uint32_t)(BN >> 3) << 17) |
+            const uint32_t fmt = FP8 ? 0u : Op16<T>::kFormat;                      // f8f6f4: 0 = E4M3; f16: 0 = F16, 1 = BF16
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
             int stage = 0;
             unsigned phase = 0;
@@ -213,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
 #pragma unroll
                     for (int h = 0; h < 2; h++)                                     // two M-halves reuse the decoded W tile
 #pragma unroll
-                        for (int j = 0; j < BK / 16; j++)                           // K = 16 per instruction = 32 bytes = 2 x 16 B
-                            umma_f16(d_tmem + (uint32_t)(h * BN), adesc + (uint64_t)(h * (128 * 128 / 16) + 2 * j),
-                                     bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0);
+                        for (int j = 0; j < 4; j++)                                 // 32 bytes of K per instruction (16 x 16-bit / 32 x 8-bit)
+                            umma<FP8>(d_tmem + (uint32_t)(h * BN), adesc + (uint64_t)(h * (128 * 128 / 16) + 2 * j),
+                                      bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0);
                     umma_commit(empty + stage);                                     // frees the stage when these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -226,10 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         // ------------------------------ weight decoders ------------------------------
         // thread = one of the tile's 256 output channels: 32 bytes of codes -> 8 x 16-byte operand chunks per k-block
         const int n_local = threadIdx.x - kDecWarp0 * 32;
-        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};                        // FP8: lo[] is the one byte table
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const uint32_t b = e < p.cb->n_entries ? Op16<T>::bits(p.cb->grid[e]) : 0u;
+            uint32_t b = 0;
+            if (e < p.cb->n_entries) b = FP8 ? e4m3_bits(__fdiv_rn(p.cb->grid[e], p.cb->pu_c)) : Op16<T>::bits(p.cb->grid[e]);
             lo[e >> 2] |= (b & 0xffu) << (8 * (e & 3));
             hi[e >> 2] |= (b >> 8) << (8 * (e & 3));
         }
@@ -240,34 +275,46 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
         const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const long long total_it = (long long)my_tiles * num_kb;
         int f_tile = blockIdx.x, f_kb = 0;                                          // position of the next fetch
-        auto fetch = [&](uint4 &a, uint4 &b) {
+        constexpr int NC = FP8 ? 4 : 2;                                             // 16-byte loads of codes per k-block
+        struct Codes { uint4 v[NC]; };
+        auto fetch = [&](Codes &c) {
             if (f_tile < num_tiles) {
                 const int n_blk = f_tile / p.m_tiles;
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.codes + (size_t)(n_blk * BN + n_local) * (size_t)(p.K / 2) + f_kb * (BK / 2));
-                a = __ldg(src); b = __ldg(src + 1);
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.codes + (size_t)(n_blk * BN + n_local) * (size_t)(p.K / 2) + f_kb * (BKE / 2));
+#pragma unroll
+                for (int i = 0; i < NC; i++) c.v[i] = __ldg(src + i);
                 if (++f_kb == num_kb) { f_kb = 0; f_tile += gridDim.x; }
             }
         };
         // kPrefetch k-blocks of codes are in flight while the current one is decoded: a global load issued and consumed in
         // the same iteration exposed ~1 us of latency per stage (profiles/r02_notes.md)
-        constexpr int kPrefetch = 3;
-        uint4 pa[kPrefetch], pb[kPrefetch];
+        constexpr int kPrefetch = FP8 ? 2 : 3;
+        Codes pf[kPrefetch];
 #pragma unroll
-        for (int u = 0; u < kPrefetch; u++) { pa[u] = make_uint4(0, 0, 0, 0); pb[u] = pa[u]; fetch(pa[u], pb[u]); }
+        for (int u = 0; u < kPrefetch; u++) {
+#pragma unroll
+            for (int i = 0; i < NC; i++) pf[u].v[i] = make_uint4(0, 0, 0, 0);
+            fetch(pf[u]);
+        }
         for (long long it = 0; it < total_it; it += kPrefetch) {
 #pragma unroll
             for (int u = 0; u < kPrefetch; u++) {
                 if (it + u < total_it) {
-                    const uint4 c0 = pa[u], c1 = pb[u];
-                    fetch(pa[u], pb[u]);                                            // the block kPrefetch ahead
+                    const Codes c = pf[u];
+                    fetch(pf[u]);                                                   // the block kPrefetch ahead
                     mbar_wait(empty + stage, phase ^ 1u);
                     unsigned char *dst = smem_b + stage * kStageB + row_off;
-                    const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(&c);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {                                   // one 32-bit word = 8 codes = one 16-byte chunk
+                    for (int j = 0; j < 8; j++) {                                   // one 16-byte chunk of the operand row
                         uint4 v;
-                        lut4(w[j], lo, hi, v.x, v.y);
-                        lut4(w[j] >> 16, lo, hi, v.z, v.w);
+                        if constexpr (FP8) {                                        // 16 codes = two 32-bit words -> 16 bytes
+                            v.x = lut4_b(w[2 * j], lo); v.y = lut4_b(w[2 * j] >> 16, lo);
+                            v.z = lut4_b(w[2 * j + 1], lo); v.w = lut4_b(w[2 * j + 1] >> 16, lo);
+                        } else {                                                    // 8 codes = one 32-bit word -> 8 x 16 bit
+                            lut4(w[j], lo, hi, v.x, v.y);
+                            lut4(w[j] >> 16, lo, hi, v.z, v.w);
+                        }
                         *reinterpret_cast<uint4 *>(dst + ((j ^ sw) << 4)) = v;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> tensor-core reads
@@ -280,6 +327,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
     } else {
         // ------------------------------ epilogue (warps 0-3 = tensor-memory lanes 32 w .. 32 w + 31) ------------------------------
         const float gmax = p.cb->gmax;
+        // FP8: the accumulator holds sum k_x k_w; unit = (c_w s_w[n]) (c_x s_x)
+        float unit = 1.0f;
+        if constexpr (FP8) unit = __fmul_rn(__fmul_rn(__fdiv_rn(p.x_alpha[0], p.x_cb->gmax), p.x_cb->pu_c), p.cb->pu_c);
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
             const int acc = 0;
@@ -287,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_linear_p4_kernel(const __gri
             float *sc = s_scale + acc * BN, *bs = s_bias + acc * BN;
             for (int c = threadIdx.x; c < BN; c += kEpiWarps * 32) {               // 128 epilogue threads, 256 channels
                 const int n = n_blk * BN + c;
-                sc[c] = __fdiv_rn(p.alpha[n], gmax);
+                sc[c] = FP8 ? __fmul_rn(__fdiv_rn(p.alpha[n], gmax), unit) : __fdiv_rn(p.alpha[n], gmax);
                 bs[c] = p.bias ? Op16<T>::to_f32(reinterpret_cast<const T *>(p.bias)[n]) : 0.0f;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");                          // the epilogue warps only
@@ -342,18 +392,18 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <typename T> int launch(const CUtensorMap &map, const GemmParams &p, int ctas, cudaStream_t st) {
+template <typename T, bool FP8> int launch(const CUtensorMap &map, const GemmParams &p, int ctas, cudaStream_t st) {
     const int smem = kStages * (kStageA + kStageB) + (2 * kStages + 4) * 8 + 16 + 4 * BN * 4 + 1024;
     static unsigned long long configured = 0ull;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 64 || !((configured >> dev) & 1ull)) {
-        e = cudaFuncSetAttribute(antq_linear_p4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(antq_linear_p4_kernel<T, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         if (dev < 64) configured |= 1ull << dev;
     }
-    antq_linear_p4_kernel<T><<<ctas, kThreads, smem, st>>>(map, p);
+    antq_linear_p4_kernel<T, FP8><<<ctas, kThreads, smem, st>>>(map, p);
     return (int)cudaGetLastError();
 }
 
@@ -381,6 +431,7 @@ extern "C" int antq_linear_p4(const void *x, const uint8_t *w_codes, const float
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ANTQ_EINVAL;
     GemmParams p;
+    p.x_alpha = nullptr; p.x_cb = nullptr;
     p.codes = w_codes; p.alpha = w_alpha; p.bias = bias; p.y = y; p.cb = (const AntqCodebook *)codebook;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.m_tiles = (int)((M + BM - 1) / BM);
@@ -388,6 +439,81 @@ extern "C" int antq_linear_p4(const void *x, const uint8_t *w_codes, const float
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     const int sms = antq_num_sms();
     const int ctas = (int)(tiles < sms ? tiles : sms);
-    return dtype == ANTQ_F16 ? launch<__half>(map, p, ctas, (cudaStream_t)stream)
-                             : launch<__nv_bfloat16>(map, p, ctas, (cudaStream_t)stream);
+    return dtype == ANTQ_F16 ? launch<__half, false>(map, p, ctas, (cudaStream_t)stream)
+                             : launch<__nv_bfloat16, false>(map, p, ctas, (cudaStream_t)stream);
+}
+
+// ---- FP8 variant: both operands as e4m3 LEVELS (integers in units of each grid's smallest level) ----
+namespace {
+template <typename T> __global__ void antq_levels_e4m3_kernel(const T *__restrict__ xq, unsigned char *__restrict__ out, const float *__restrict__ alpha,
+                                                              const AntqCodebook *__restrict__ cb, long long n) {
+    typedef AntqType<T> A;
+    // x_q = RN_T(fl32(k c s)) -> k = rint(x_q / (c s)): |k| <= 448 and T has >= 8 significant bits, so rint is exact
+    const float kx = __fdiv_rn(1.0f, __fmul_rn(__fdiv_rn(alpha[0], cb->gmax), cb->pu_c));
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    if (i0 + 16 <= n && ((uintptr_t)(xq + i0) % 16 == 0) && ((uintptr_t)(out + i0) % 16 == 0) && sizeof(T) == 2) {
+        T v[16];
+        reinterpret_cast<uint4 *>(v)[0] = antq_ldg_stream(reinterpret_cast<const uint4 *>(xq + i0));
+        reinterpret_cast<uint4 *>(v)[1] = antq_ldg_stream(reinterpret_cast<const uint4 *>(xq + i0) + 1);
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 16; e++) w[e >> 2] |= e4m3_bits(rintf(__fmul_rn(A::to_f32(v[e]), kx))) << (8 * (e & 3));
+        *reinterpret_cast<uint4 *>(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (long long i = i0; i < n && i < i0 + 16; i++) out[i] = (unsigned char)e4m3_bits(rintf(__fmul_rn(A::to_f32(xq[i]), kx)));
+    }
+}
+}  // namespace
+
+extern "C" int antq_levels_e4m3(const void *x_q, uint8_t *levels, const float *alpha, int64_t n, int dtype, const void *codebook,
+                                const antq_codebook_info *info, void *stream) {
+    if (n < 0 || !info) return ANTQ_EINVAL;
+    if (n == 0) return 0;
+    if (!x_q || !levels || !alpha || !codebook) return ANTQ_EINVAL;
+    if (!(info->flags & ANTQ_CB_PU_E4M3)) return ANTQ_ENOTSUP;
+    const unsigned ctas = (unsigned)((n / 16 + 256) / 256);
+    const AntqCodebook *cb = (const AntqCodebook *)codebook;
+    switch (dtype) {
+        case ANTQ_F16: antq_levels_e4m3_kernel<__half><<<ctas, 256, 0, (cudaStream_t)stream>>>((const __half *)x_q, levels, alpha, cb, n); break;
+        case ANTQ_BF16: antq_levels_e4m3_kernel<__nv_bfloat16><<<ctas, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x_q, levels, alpha, cb, n); break;
+        case ANTQ_F32: antq_levels_e4m3_kernel<float><<<ctas, 256, 0, (cudaStream_t)stream>>>((const float *)x_q, levels, alpha, cb, n); break;
+        default: return ANTQ_EINVAL;
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int antq_linear_p4_fp8(const uint8_t *x_levels, const float *x_alpha, const void *x_codebook, const antq_codebook_info *x_info,
+                                  const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M, int64_t N, int64_t K,
+                                  int out_dtype, const void *w_codebook, const antq_codebook_info *w_info, int flags, void *stream) {
+    if (M < 0 || N < 0 || K < 0 || !w_info || !x_info) return ANTQ_EINVAL;
+    if (M == 0 || N == 0) return 0;
+    if (!x_levels || !x_alpha || !x_codebook || !w_codes || !w_alpha || !y || !w_codebook) return ANTQ_EINVAL;
+    if (out_dtype != ANTQ_F16 && out_dtype != ANTQ_BF16) return ANTQ_ENOTSUP;
+    if ((flags & ANTQ_FLAG_OVP) && w_info->n_entries > w_info->n_normal) return ANTQ_ENOTSUP;
+    if (!(w_info->flags & ANTQ_CB_PU_E4M3) || !(x_info->flags & ANTQ_CB_PU_E4M3)) return ANTQ_ENOTSUP;   // levels must be exact in e4m3
+    if (w_info->n_entries > 16 || K % (2 * BK) || N % BN || K == 0 || M > 0x7fffffffLL / 2 || N > 0x7fffffffLL / 2) return ANTQ_ENOTSUP;
+    if ((uintptr_t)x_levels % 16 || (uintptr_t)y % 16 || (uintptr_t)w_codes % 16) return ANTQ_EALIGN;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return ANTQ_ENOTSUP;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)K};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * BK), (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(x_levels), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ANTQ_EINVAL;
+    GemmParams p;
+    p.codes = w_codes; p.alpha = w_alpha; p.bias = bias; p.y = y; p.cb = (const AntqCodebook *)w_codebook;
+    p.x_alpha = x_alpha; p.x_cb = (const AntqCodebook *)x_codebook;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.m_tiles = (int)((M + BM - 1) / BM);
+    p.n_tiles = (int)(N / BN);
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    const int sms = antq_num_sms();
+    const int ctas = (int)(tiles < sms ? tiles : sms);
+    return out_dtype == ANTQ_F16 ? launch<__half, true>(map, p, ctas, (cudaStream_t)stream)
+                                 : launch<__nv_bfloat16, true>(map, p, ctas, (cudaStream_t)stream);
 }

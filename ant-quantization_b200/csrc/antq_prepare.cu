@@ -91,7 +91,15 @@ __device__ int antq_pu_analyze(const float *lev, int L, int *ku, AntqCodebook *c
     int xc = 0;
     if (kmax <= 400.0f * step_hi && -kmin <= 400.0f * step_lo) xc |= ANTQ_CB_PU_XC16;
     if (kmax <= 48.0f * step_hi && -kmin <= 48.0f * step_lo) xc |= ANTQ_CB_PU_XCBF;
-    return ANTQ_CB_PU | (uniform ? ANTQ_CB_PU_UNIFORM : 0) | xc;
+    // Is every k exactly representable in FP8 e4m3 (1 + 3 significant bits, |k| <= 448)?  Then a 4-bit tensor can be fed
+    // to the FP8 tensor cores as levels without any rounding (antq_gemm.cu).
+    bool e4m3 = kmax <= 448.0f && -kmin <= 448.0f;
+    for (int i = 0; i < nu && e4m3; i++) {
+        int e = 0;
+        while ((2 << e) <= ku[i]) e++;
+        if (e > 3 && (ku[i] & ((1 << (e - 3)) - 1))) e4m3 = false;
+    }
+    return ANTQ_CB_PU | (uniform ? ANTQ_CB_PU_UNIFORM : 0) | xc | (e4m3 ? ANTQ_CB_PU_E4M3 : 0);
 }
 
 __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float *__restrict__ grid, int k_normal,

@@ -107,6 +107,8 @@ int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, 
 #define ANTQ_CB_PU_XC16  128  /* PU: the clamp to [kmin, kmax] may be done on the fp16 INPUT (packed min / max): the largest
                                  level is far enough from its lower midpoint for an fp16-rounded bound */
 #define ANTQ_CB_PU_XCBF  256  /* the same for bf16 inputs */
+#define ANTQ_CB_PU_E4M3  512  /* PU and every level / pu_c is exactly representable in FP8 e4m3 (all 4-bit int / flint / pot /
+                                 float grids): the FP8 tensor-core path applies */
 
 /* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
  * `info` (host pointer, may be NULL) lets the call pick the row-table kernel
@@ -193,6 +195,17 @@ int antq_calibrate(const void *x, int64_t rows, int64_t cols, int dtype, int alp
 int antq_linear_p4(const void *x, const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M,
                    int64_t N, int64_t K, int dtype, const void *codebook, const antq_codebook_info *info, int flags,
                    void *stream);
+
+/* FP8 variant for W4A4: both operands travel as e4m3 LEVELS (level / smallest positive level: small integers, exact in
+ * e4m3 when ANTQ_CB_PU_E4M3 is set), tcgen05.mma kind::f8f6f4 runs at twice the 16-bit rate, the integer products are
+ * exact in the fp32 accumulator and both scales are applied in the epilogue:
+ *   y[m, n] = (sum_k kx[m, k] kw[n, k]) * (c_x alpha_x / max(grid_x)) * (c_w alpha_w[n] / max(grid_w)) + bias[n].
+ * antq_levels_e4m3 turns a fake-quantized activation (per-tensor alpha) into its level bytes.  K % 128 == 0, N % 256 == 0. */
+int antq_levels_e4m3(const void *x_q, uint8_t *levels, const float *alpha, int64_t n, int dtype, const void *codebook,
+                     const antq_codebook_info *info, void *stream);
+int antq_linear_p4_fp8(const uint8_t *x_levels, const float *x_alpha, const void *x_codebook, const antq_codebook_info *x_info,
+                       const uint8_t *w_codes, const float *w_alpha, const void *bias, void *y, int64_t M, int64_t N, int64_t K,
+                       int out_dtype, const void *w_codebook, const antq_codebook_info *w_info, int flags, void *stream);
 
 /* ---- host-buffer path (what a CPU caller of the reference would use) ---- */
 typedef struct antq_host_ctx antq_host_ctx;

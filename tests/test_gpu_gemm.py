@@ -105,10 +105,57 @@ with torch.no_grad():
     dropped = q._wc_val is None
     y4 = q(x.float().half())
     L.FUSED_LINEAR = False
+L.FUSED_LINEAR = True; L.FUSED_FP8 = False
+with torch.no_grad():
+    y5 = q(x)                                    # 16-bit operand variant
+L.FUSED_LINEAR = False; L.FUSED_FP8 = True
+RESULT["rel16"] = float((y5.float() - y1.float()).norm() / y1.float().norm())
 rel = float((y2.float() - y1.float()).norm() / y1.float().norm())
 RESULT.update(rel=rel, hit=bool(hit), same=bool(torch.equal(y2, y3) and torch.equal(y3, y4)), codes_bytes=codes_bytes,
               train_unfused=bool(torch.equal(yt, y1)), dropped=bool(dropped), shape=list(y2.shape))
 ''', timeout=600)
     assert res["shape"] == [4, 96, 512] and res["hit"] and res["same"] and res["dropped"] and res["train_unfused"], res
     assert res["codes_bytes"] == 512 * 1024 // 2, res
-    assert res["rel"] < 2e-3, res
+    assert res["rel"] < 2e-3 and res["rel16"] < 2e-3, res
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("wkind,wsigned,xkind,xsigned", [("flint", True, "flint", False), ("int", True, "int", True), ("pot", True, "flint", True)])
+@pytest.mark.parametrize("M,N,K", [(300, 256, 512), (2048, 1024, 4096)])
+def test_linear_p4_fp8_is_exact_in_levels(antq, M, N, K, wkind, wsigned, xkind, xsigned, dtype):
+    """W4A4 on the FP8 tensor cores: operands travel as e4m3 levels (small integers), so the accumulator is an exact
+    integer and the output is reproducible bit for bit on the host: y = RN(fl32(acc * scale_n + bias_n))."""
+    from antq import _lib
+    w, wq, codes, alpha, cb = _weights(antq, N, K, wkind, wsigned, dtype, 5)
+    xgrid = orc.ant_grid(xkind, 4, xsigned)
+    xcb = antq.prepare_codebook(torch.from_numpy(xgrid).to(dev()))
+    assert (cb.info.flags & _lib.CB_PU_E4M3) and (xcb.info.flags & _lib.CB_PU_E4M3)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x = torch.randn(M, K, generator=g).to(dtype).to(dev())
+    if not xsigned:
+        x = x.abs()
+    xa = (x.float().abs().max() * 0.8).reshape(1)
+    xq = antq.fakequant(x, xa, xcb, False)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dtype).to(dev())
+    y = antq.linear_p4_fp8(xq, xa, xcb, codes, alpha, cb, N, bias=bias)
+    # host replica: integer levels, exact integer GEMM in float64, the epilogue's fp32 operations in order
+    f32 = np.float32
+    cx = f32(xgrid[xgrid > 0].min())
+    wgrid = orc.ant_grid(wkind, 4, wsigned)
+    cw = f32(wgrid[wgrid > 0].min())
+    sx = f32(f32(xa.item()) / f32(xgrid.max()))
+    kx = np.rint(xq.float().cpu().numpy() / f32(sx * cx)).astype(np.float64)
+    sw = (alpha.cpu().numpy().astype(f32) / f32(cb.info.gmax)).astype(f32)
+    kw = np.rint(wq.float().cpu().numpy() / (sw[:, None] * cw)).astype(np.float64)
+    assert np.abs(kx).max() <= 448 and np.abs(kw).max() <= 448
+    acc = kx @ kw.T                                                       # exact: |acc| < 2^24
+    assert np.abs(acc).max() < 2 ** 24
+    unit = f32(f32(sx * cx) * cw)
+    sc = (sw * unit).astype(f32)
+    ref32 = (acc * sc[None, :].astype(np.float64) + bias.float().cpu().numpy().astype(np.float64)[None, :]).astype(f32)   # one rounding = fmaf
+    ref = torch.from_numpy(ref32).to(dtype)
+    assert torch.equal(y.cpu().view(torch.int16), ref.view(torch.int16)), int((y.cpu().view(torch.int16) != ref.view(torch.int16)).sum())
+    # and it IS the layer's F.linear on the fake-quantized operands, up to their 16-bit roundings
+    lib = F.linear(xq.float(), wq.float(), bias.float())
+    err = (y.float() - lib).norm() / lib.norm()
+    assert float(err) < (1.5e-3 if dtype == torch.float16 else 8e-3), float(err)

@@ -48,9 +48,15 @@ for dt in (torch.float16, torch.bfloat16):
         def requant_then():                       # what the reference does every forward: re-fake-quantize, then GEMM
             k = i[0] = (i[0] + 1) % nb
             return F.linear(xs[k], antq.fakequant(ws[k], als[k], cb, True))
+        xcb = antq.prepare_codebook(codebooks.ant_grid("flint", 4, False).to(dev))
+        xas = [x.float().abs().max().reshape(1) * 0.8 for x in xs]
+        xqs = [antq.fakequant(x.abs(), a, xcb, False) for x, a in zip(xs, xas)]
+        def fused_fp8():                          # W4A4 as e4m3 levels (includes the level-conversion kernel)
+            k = i[0] = (i[0] + 1) % nb
+            return antq.linear_p4_fp8(xqs[k], xas[k], xcb, cds[k], als[k], cb, N)
         fl = 2.0 * M * N * K
         r = {"M": M, "N": N, "K": K, "dtype": str(dt).split(".")[1]}
-        for name, fn in (("fused_tcgen05", fused), ("cublas_on_fp16_weight", cublas), ("decode_p4+cublas", decode_then),
+        for name, fn in (("fused_tcgen05_fp8_w4a4", fused_fp8), ("fused_tcgen05", fused), ("cublas_on_fp16_weight", cublas), ("decode_p4+cublas", decode_then),
                          ("fakequant+cublas", requant_then)):
             us = timeit(fn, 20)
             r[name] = {"us": round(us, 1), "tflops": round(fl / us / 1e6, 1), "frac_of_measured_bf16_peak": round(fl / us / 1e6 / peak, 3)}
