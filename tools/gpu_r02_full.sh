@@ -1,7 +1,7 @@
 # Round-2 full GPU validation + measurements (run under gpurun from the repo root).
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests/test_gpu_gemm.py -q -x -p no:cacheprovider > gpurun_out/r02_pytest_gemm.log 2>&1; echo GEMM_RC=$?; tail -5 gpurun_out/r02_pytest_gemm.log
-python -m pytest tests -m gpu -q --durations=5 -p no:cacheprovider --deselect tests/test_gpu_gemm.py > gpurun_out/r02_pytest.log 2>&1; tail -12 gpurun_out/r02_pytest.log
+python -m pytest tests -m gpu -q --durations=5 -p no:cacheprovider --ignore tests/test_gpu_gemm.py > gpurun_out/r02_pytest.log 2>&1; tail -12 gpurun_out/r02_pytest.log
 timeout 300 python tools/gemm_bench.py > gpurun_out/r02_gemm_bench.log 2>&1; tail -4 gpurun_out/r02_gemm_bench.log | cut -c1-420
 python bench.py --steps 50 --warmup 5 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; cat gpurun_out/r02_bench.json; tail -3 gpurun_out/r02_bench.err
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r02_bench_reference.json 2>/dev/null; cat gpurun_out/r02_bench_reference.json
