@@ -22,7 +22,11 @@ __device__ __forceinline__ bool hi_wins(float d, float lo, float hi, bool tie_hi
 
 // Piecewise-uniform analysis (one thread; mirrors tests/pu_model.py::analyze line for line).  `ku` is scratch for the
 // union of magnitudes in units of c.  Returns ANTQ_CB_PU (| ANTQ_CB_PU_UNIFORM) and fills the pu_* fields, or 0.
-__device__ int antq_pu_analyze(const float *lev, int L, int *ku, AntqCodebook *cb) {
+__device__ int antq_pu_analyze(const float *lev, const int *lcode, int L, int *ku, AntqCodebook *cb) {
+    // the closed form settles near-midpoint elements by comparing the two neighbouring levels with "the upper one wins a
+    // tie": that is the scan's rule (later entry wins) only when the scan meets the levels in ascending order
+    for (int r = 0; r + 1 < L; r++)
+        if (lcode[r] >= lcode[r + 1]) return 0;
     int zero = -1, npos = 0;
     for (int r = 0; r < L; r++) {
         if (lev[r] == 0.0f) zero = r;
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
         if (ovp_index < 0 && !sym) { /* no outlier level at all: OVP is a no-op */ }
         if (ovp_ok) flags |= ANTQ_CB_OVP_OK;
         cb->pu_c = 0.0f; cb->pu_inv_c = 0.0f; cb->pu_kmin = 0.0f; cb->pu_kmax = 0.0f;
-        if (sep && ste) flags |= antq_pu_analyze(lev, L, keep, cb);     // keep[] is free by now: scratch
+        if (sep && ste) flags |= antq_pu_analyze(lev, lcode, L, keep, cb);     // keep[] is free by now: scratch
 
         cb->n_entries = K;
         cb->n_normal = k_normal;

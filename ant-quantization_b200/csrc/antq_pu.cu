@@ -36,6 +36,8 @@ constexpr int kNS = 2 * kNC;              // two private stages per warp
 constexpr int kChunkMax = 4096;
 constexpr int kThreads = kNC * 32;
 constexpr int kListMax = 512;             // per-warp work list of elements to redo exactly (per chunk)
+constexpr int kQCap = 512;                // CTA-wide queue of near-midpoint vectors settled after the last chunk
+struct __align__(16) PuQEntry { uint4 raw; long long v; float s, kx; };
 
 struct PuParams {
     const void *x;
@@ -48,13 +50,14 @@ struct PuParams {
     float gmax, lim;
     int debug;
     // short kernel
-    unsigned nvec, cols_vec;
+    unsigned nvec, cols_vec, cols_magic;
     int cols_shift;
 };
 
 struct PuK {                               // the codebook's closed-form constants (AntqCodebook::pu_*)
     float c, inv_c, kmin, kmax;
     float xc_lo, xc_hi;                    // x-space clamp: (kmin - 0.4 step_top) and (kmax + 0.4 step_top), in units of c
+    float hd_c;                            // uniform grids behind the x-space clamp: 0.5 - (max|k| + 1) 2^-19, one constant
 };
 __device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
     PuK k;
@@ -65,6 +68,7 @@ __device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
     const float step_lo = __fmul_rn(cb->pu_tab[(__float_as_uint(k.kmin) & 0x7fffffffu) >> 23].x, 7.94728597e-08f);
     k.xc_hi = __fadd_rn(k.kmax, __fmul_rn(0.4f, step_hi));
     k.xc_lo = __fsub_rn(k.kmin, __fmul_rn(0.4f, step_lo));
+    k.hd_c = __fmaf_rn(__fadd_rn(fmaxf(k.kmax, -k.kmin), 1.0f), -1.9073486328125e-06f, 0.5f);
     return k;
 }
 
@@ -100,13 +104,14 @@ __device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const Pu
 
 // The closed form for one element.  `flag` accumulates "redo me exactly".  CLAMP = false: the input was already clamped
 // in x-space (packed min / max on the 16-bit pairs), so t cannot round beyond [kmin, kmax].
-template <bool UNIFORM, bool CLAMP>
+template <bool UNIFORM, bool CLAMP, bool HDC>
 __device__ __forceinline__ float pu_quant(float xf, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
     const float t = __fmul_rn(xf, r.kx);
     float M, hd;
     if (UNIFORM) {
         M = 12582912.0f;                                              // 1.5 * 2^23: step 1 everywhere
-        hd = __fmaf_rn(fabsf(t), -1.9073486328125e-06f, 0.5f);        // 0.5 - |t| 2^-19
+        // 0.5 - |t| 2^-19; behind the x-space clamp |t| <= max|k| + 0.4, so one constant (a little more conservative) does
+        hd = (CLAMP || !HDC) ? __fmaf_rn(fabsf(t), -1.9073486328125e-06f, 0.5f) : K.hd_c;
     } else {
         const float2 md = tab[__float_as_uint(t) >> 23];              // sign + exponent index a 512-entry table
         M = md.x; hd = md.y;                                          // step / 2 - delta_e
@@ -193,19 +198,21 @@ template <> struct PuIO<__nv_bfloat16> {
     }
 };
 
-// One 16-byte vector through the closed form; `flag` = some element needs the exact redo.
+// One 16-byte vector through the closed form.  `near` = some element lies within delta of a midpoint (settled by
+// pu_vec_exact); `wild` = some element is outside the window in which the closed form is proven (|d| beyond the STE
+// window, NaN, Inf: the literal path).
 // XC (16-bit types): clamp the INPUT pairs with two packed min / max instead of every t with two FMNMX.
-template <typename T, bool UNIFORM, bool XC>
-__device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab, bool &flag) {
+template <typename T, bool UNIFORM, bool XC, bool HDC = false>
+__device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab, bool &near, bool &wild) {
     constexpr int VEC = PuIO<T>::VEC;
     float f[VEC], o[VEC];
-    bool fl = false;
+    bool fn = false, fw = false;
     if constexpr (sizeof(T) == 2) {
         typedef typename PuPack<T>::v2 v2;
         // one packed NaN-propagating max of |x| per vector against the exact window
         const v2 a = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.x)), __habs2(PuPack<T>::from_u32(raw.y)));
         const v2 b = __hmax2_nan(__habs2(PuPack<T>::from_u32(raw.z)), __habs2(PuPack<T>::from_u32(raw.w)));
-        fl |= __hle2_mask(__hmax2_nan(a, b), PuPack<T>::from_u32(r.xl2)) != 0xffffffffu;
+        fw = __hle2_mask(__hmax2_nan(a, b), PuPack<T>::from_u32(r.xl2)) != 0xffffffffu;
         if constexpr (XC) {
             const v2 lo = PuPack<T>::from_u32(r.xlo2), hi = PuPack<T>::from_u32(r.xhi2);
             uint4 c;
@@ -222,15 +229,48 @@ __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const P
     }
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
-        o[e] = pu_quant<UNIFORM, !(XC && sizeof(T) == 2)>(f[e], r, K, tab, fl);
-        if (sizeof(T) == 4) fl |= !(fabsf(f[e]) <= r.xl);             // outside the exact window, NaN, Inf
+        o[e] = pu_quant<UNIFORM, !(XC && sizeof(T) == 2), HDC>(f[e], r, K, tab, fn);
+        if (sizeof(T) == 4) fw |= !(fabsf(f[e]) <= r.xl);             // outside the exact window, NaN, Inf
     }
-    flag = fl;
+    near = fn;
+    wild = fw;
     return PuIO<T>::pack(o);
 }
 
-// Which elements of a vector need the exact redo (bit e), recomputed with the closed form's own tests -- unrolled, in
-// registers (an indexed loop over f[] would put the vector in local memory and make the redo latency-bound).
+// The same vector settled exactly, element by element, WITHOUT a search: t lies between the level it rounds to (mf) and
+// that level's neighbour on t's side (mf +- the octave's step), so the scan's winner is one of the two -- and which one
+// is the scan's own comparison of rounded distances on d = x / s (true division), the upper level winning a tie
+// (ascending grids: the later entry).  Valid for every element inside the window, near a midpoint or not; elements
+// outside it get garbage here and are rewritten by the literal path.  Proof sketch: |t - d / c| is a few ulps, far
+// below step / 2, so rank(d) is the index of one of the two candidates (ANTQ_CB_WELLSEP: adjacent thresholds decide).
+template <bool UNIFORM>
+__device__ __forceinline__ float pu_elem_exact(const float xf, const float s, const float kx, const PuK &K, const float2 *tab) {
+    const float t = __fmul_rn(xf, kx);
+    float M = 12582912.0f, step = 1.0f;
+    if (!UNIFORM) {
+        M = tab[__float_as_uint(t) >> 23].x;                          // 1.5 * 2^23 * step
+        step = __uint_as_float((__float_as_uint(M) & 0x7f800000u) - (23u << 23));
+    }
+    const float mf = __fsub_rn(__fadd_rn(t, M), M);
+    const float rr = __fsub_rn(t, mf);
+    const float oth = __fadd_rn(mf, copysignf(step, rr));
+    const float k1 = fminf(fmaxf(mf, K.kmin), K.kmax), k2 = fminf(fmaxf(oth, K.kmin), K.kmax);
+    const float ql = __fmul_rn(fminf(k1, k2), K.c), qh = __fmul_rn(fmaxf(k1, k2), K.c);
+    const float d = __fdiv_rn(xf, s);
+    const float dl = fabsf(__fsub_rn(d, ql)), dh = fabsf(__fsub_rn(d, qh));
+    return antq_ste_rescale(dh <= dl ? qh : ql, d, s);
+}
+template <typename T, bool UNIFORM>
+__device__ __noinline__ uint4 pu_vec_exact(const uint4 raw, const float s, const float kx, const PuK K, const float2 *tab) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC], o[VEC];
+    PuIO<T>::unpack(raw, f);
+#pragma unroll
+    for (int e = 0; e < VEC; e++) o[e] = pu_elem_exact<UNIFORM>(f[e], s, kx, K, tab);
+    return PuIO<T>::pack(o);
+}
+
+// Which elements of a vector need the literal path (bit e): those outside the exact window (NaN and Inf included).
 template <typename T, bool UNIFORM>
 __device__ __forceinline__ unsigned pu_vec_mask(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab) {
     constexpr int VEC = PuIO<T>::VEC;
@@ -238,12 +278,7 @@ __device__ __forceinline__ unsigned pu_vec_mask(const uint4 raw, const PuRow &r,
     PuIO<T>::unpack(raw, f);
     unsigned m = 0;
 #pragma unroll
-    for (int e = 0; e < VEC; e++) {
-        bool fl = false;
-        (void)pu_quant<UNIFORM, true>(f[e], r, K, tab, fl);
-        fl |= !(fabsf(f[e]) <= r.xl);
-        m |= (fl ? 1u : 0u) << e;
-    }
+    for (int e = 0; e < VEC; e++) m |= (!(fabsf(f[e]) <= r.xl) ? 1u : 0u) << e;
     return m;
 }
 
@@ -265,14 +300,129 @@ __device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, co
     }
 }
 
+// Exact redo of one chunk, dense: the flagged ELEMENTS of the whole chunk are compacted into a per-warp list and redone
+// one per lane (a row with representable ties can flag a few percent of a chunk; redoing them vector by vector inside
+// their owner lane serialised a warp for tens of microseconds: profiles/r02_notes.md).  redo bit j: vector j * 32 + lane.
+// Only the WILD elements come here (outside the exact window, NaN, Inf, rows with a bad scale): near-midpoint elements
+// are settled by pu_vec_exact in their owner lane.
+template <typename T, bool UNIFORM>
+__device__ __noinline__ void pu_redo_chunk(const AntqCodebook *__restrict__ cb, const PuExact X, const uint4 *sv, T *og,
+                                           const int nvec, const PuRow r, const PuK K, const float2 *tab, const unsigned redo,
+                                           unsigned short *redo_list, const int lane) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    unsigned long long em = 0;                                        // bit 8 j + e: element e of vector j * 32 + lane
+    if (r.ok) {
+        for (int j = 0; j * 32 + lane < nvec; j++)
+            if ((redo >> j) & 1u)
+                em |= (unsigned long long)pu_vec_mask<T, UNIFORM>(sv[j * 32 + lane], r, K, tab) << (8 * j);
+    }
+    const int cnt = __popcll(em);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool overflow = !r.ok || total > kListMax;
+    if (!overflow) {
+        int pos = incl - cnt;
+        while (em) {
+            const int b = __ffsll((long long)em) - 1;
+            em &= em - 1;
+            redo_list[pos++] = (unsigned short)((lane << 6) | b);
+        }
+        __syncwarp();          // list complete; the fast path's vector stores are ordered before the rewrites
+        for (int i = lane; i < total; i += 32) {
+            const unsigned it = redo_list[i];
+            const int v = (int)((it & 63u) >> 3) * 32 + (int)(it >> 6), e = (int)(it & 7u);
+            const float xf = A::to_f32(reinterpret_cast<const T *>(sv + v)[e]);
+            og[(long long)v * VEC + e] = pu_exact_elem<T>(cb, X, xf, r.s);
+        }
+        __syncwarp();          // the list is rewritten by this warp's next chunk
+    } else {
+        for (int j = 0; j * 32 + lane < nvec; j++) {
+            if ((redo >> j) & 1u) {
+                const int v = j * 32 + lane;
+                pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void pu_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(antq_smem_u32(bar)) : "memory");
 }
 
+// Row constants as one 16-byte word.  A bad scale (zero, Inf, NaN) is folded into the window bound (NaN: every vector
+// of the row fails the window test and takes the literal path) plus one bit for the redo.
+template <typename T> __device__ __forceinline__ uint4 pu_row_pack(const PuRow &r) {
+    uint4 w;
+    w.x = __float_as_uint(r.s);
+    w.y = __float_as_uint(r.kx);
+    if constexpr (sizeof(T) == 2) {
+        w.z = (r.ok ? (r.xl2 & 0xffffu) : 0x7fffu) | (r.ok ? 0x10000u : 0u);
+        w.w = (r.xlo2 & 0xffffu) | (r.xhi2 << 16);
+    } else {
+        w.z = r.ok ? __float_as_uint(r.xl) : 0x7fc00000u;
+        w.w = r.ok ? 1u : 0u;
+    }
+    return w;
+}
+template <typename T> __device__ __forceinline__ PuRow pu_row_unpack(const uint4 w) {
+    PuRow r;
+    r.s = __uint_as_float(w.x);
+    r.kx = __uint_as_float(w.y);
+    if constexpr (sizeof(T) == 2) {
+        r.xl2 = __byte_perm(w.z, 0, 0x1010);
+        r.ok = (w.z >> 16) != 0;
+        r.xlo2 = __byte_perm(w.w, 0, 0x1010);
+        r.xhi2 = __byte_perm(w.w, 0, 0x3232);
+        r.xl = 0.0f;                                                  // the redo path recomputes it (pu_row_xl)
+    } else {
+        r.xl = __uint_as_float(w.z);
+        r.ok = w.w != 0;
+        r.xl2 = r.xlo2 = r.xhi2 = 0;
+    }
+    return r;
+}
+__device__ __forceinline__ float pu_row_xl(const PuParams &p, float s) {
+    return __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);
+}
+
+struct PuTileRows {                          // which rows a tile touches and how a vector finds its row
+    unsigned row0, nrows, vbase;             // first row, number of rows, first vector of row0
+};
+__device__ __forceinline__ unsigned pu_row_of(const PuParams &p, unsigned v) {
+    return p.cols_shift >= 0 ? v >> p.cols_shift : v / p.cols_vec;
+}
+__device__ __forceinline__ PuTileRows pu_tile_rows(const PuParams &p, unsigned v0, unsigned vlast) {
+    PuTileRows t;
+    t.row0 = 0; t.nrows = 1; t.vbase = 0;
+    if (p.alpha_per_row) {
+        t.row0 = pu_row_of(p, v0);
+        t.nrows = pu_row_of(p, vlast) - t.row0 + 1;
+        t.vbase = t.row0 * p.cols_vec;
+    }
+    return t;
+}
+// row of vector v relative to the tile's first row: (v - vbase) / cols_vec with v - vbase < kTileVec + cols_vec <= 255
+// and cols_vec <= 127: the 16-bit reciprocal (p.cols_magic = 65536 / cols_vec + 1) is exact there.
+__device__ __forceinline__ unsigned pu_row_local(const PuParams &p, const PuTileRows &t, unsigned v) {
+    if (!p.alpha_per_row) return 0;
+    const unsigned off = v - t.vbase;
+    return p.cols_shift >= 0 ? off >> p.cols_shift : (off * p.cols_magic) >> 16;
+}
+
 // ==================================================================================================
 // Long rows / per-tensor: persistent CTAs, TMA-staged chunks.
+// SHORT: rows shorter than a chunk (scale groups, 1x1-conv weights; 2 .. 127 vectors per row).  The tensor is chunked
+// flat; the rows a chunk touches (<= kRowsPerChunk) get their constants computed once, one row per lane, into a per-warp
+// table, and every vector fetches its row's constants with one LDS.128.
 // ==================================================================================================
-template <typename T, bool UNIFORM, bool XC>
+constexpr int kRowsPerChunk = 132;        // 256 vectors / 2 per row + straddle, rounded up
+template <typename T, bool UNIFORM, bool XC, bool SHORT>
 __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
@@ -282,7 +432,11 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     float *x_lev = x_thr + ANTQ_MAX_GRID;
     uint64_t *full = reinterpret_cast<uint64_t *>(x_lev + ANTQ_MAX_GRID);
     unsigned *next_k = reinterpret_cast<unsigned *>(full + kNS);
-    unsigned short *redo_list = reinterpret_cast<unsigned short *>(next_k + 4) + (size_t)(threadIdx.x >> 5) * kListMax;
+    unsigned *qcount = next_k + 1;
+    PuQEntry *queue = reinterpret_cast<PuQEntry *>(next_k + 4);
+    unsigned short *redo_list = reinterpret_cast<unsigned short *>(queue + kQCap) + (size_t)(threadIdx.x >> 5) * kListMax;
+    uint4 *rows_s = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(queue + kQCap) + (size_t)kNC * kListMax) +
+                    (size_t)(threadIdx.x >> 5) * kRowsPerChunk;       // SHORT only (not allocated otherwise)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned c_begin = blockIdx.x * p.chunks_per_cta + min(blockIdx.x, p.chunks_rem);
@@ -292,23 +446,35 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
 
     asm volatile("griddepcontrol.launch_dependents;");                // programmatic dependent launch, as antq_stream.cu
     if (threadIdx.x < kNS) antq_mbar_init(full + threadIdx.x, 1);
-    if (threadIdx.x == 0) *next_k = 0;
+    if (threadIdx.x == 0) { *next_k = 0; *qcount = 0; }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    struct Geo { long long base; int nvec, tail; unsigned row; float alpha; };
+    struct Geo { long long base; int nvec, tail; unsigned row; float alpha, alpha1; PuTileRows tr; };
     auto geo_of = [&](int k) {
         Geo g;
         const unsigned c = c_begin + (unsigned)k;
-        const unsigned row = p.cpr_shift >= 0 ? c >> p.cpr_shift : c / cpr;
-        const long long col0 = (long long)(c - row * cpr) * p.chunk_elems;
-        const long long remain = p.cols - col0;
-        const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
-        g.nvec = n_el / VEC;
-        g.tail = n_el - g.nvec * VEC;
-        g.base = (long long)row * p.cols + col0;
-        g.row = row;
-        g.alpha = 0.0f;
+        g.alpha = 0.0f; g.alpha1 = 0.0f;
+        g.tr.row0 = 0; g.tr.nrows = 1; g.tr.vbase = 0;
+        if constexpr (SHORT) {
+            const unsigned cv = (unsigned)p.chunk_elems / VEC;
+            const unsigned v0 = c * cv;
+            const unsigned left = p.nvec - v0;
+            g.nvec = (int)(left < cv ? left : cv);
+            g.tail = 0;
+            g.base = (long long)v0 * VEC;
+            g.tr = pu_tile_rows(p, v0, v0 + (unsigned)g.nvec - 1u);
+            g.row = g.tr.row0;
+        } else {
+            const unsigned row = p.cpr_shift >= 0 ? c >> p.cpr_shift : c / cpr;
+            const long long col0 = (long long)(c - row * cpr) * p.chunk_elems;
+            const long long remain = p.cols - col0;
+            const int n_el = (int)(remain < p.chunk_elems ? remain : p.chunk_elems);
+            g.nvec = n_el / VEC;
+            g.tail = n_el - g.nvec * VEC;
+            g.base = (long long)row * p.cols + col0;
+            g.row = row;
+        }
         return g;
     };
     auto request = [&](Geo &g, int stage) {
@@ -323,7 +489,13 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             }
         }
         // the row's alpha travels with the request: its latency hides behind the bulk copy
-        g.alpha = __ldg(p.alpha + (p.alpha_per_row ? g.row : 0u));
+        if constexpr (SHORT) {
+            // the first two rows of this lane (64 rows per chunk: groups of 4 vectors and longer); more are loaded late
+            if ((unsigned)lane < g.tr.nrows) g.alpha = __ldg(p.alpha + (p.alpha_per_row ? g.tr.row0 + lane : 0u));
+            if ((unsigned)lane + 32u < g.tr.nrows) g.alpha1 = __ldg(p.alpha + g.tr.row0 + lane + 32u);
+        } else {
+            g.alpha = __ldg(p.alpha + (p.alpha_per_row ? g.row : 0u));
+        }
     };
     auto claim = [&]() {
         int k = 0;
@@ -332,7 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     };
 
     Geo cur;
-    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.row = 0; cur.alpha = 0.0f;
+    cur.base = 0; cur.nvec = 0; cur.tail = 0; cur.row = 0; cur.alpha = 0.0f; cur.alpha1 = 0.0f;
+    cur.tr.row0 = 0; cur.tr.nrows = 0; cur.tr.vbase = 0;
     int k = claim();
     if (k < n) {
         cur = geo_of(k);
@@ -358,14 +531,27 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
             cur = geo_of(kn);
             request(cur, warp + (slot ^ 1) * kNC);
         }
-        const PuRow r = pu_row<T>(g.alpha, p, K, false);
+        PuRow r;
+        if constexpr (SHORT) {
+            // this chunk's row table (before waiting for the data: only the alphas are needed)
+            for (unsigned i = lane, a = 0; i < g.tr.nrows; i += 32, a++) {
+                const float al = a == 0 ? g.alpha : a == 1 ? g.alpha1 : __ldg(p.alpha + g.tr.row0 + i);
+                rows_s[i] = pu_row_pack<T>(pu_row<T>(al, p, K, true));
+            }
+            r.s = 1.0f; r.kx = 1.0f; r.xl = 0.0f; r.xl2 = r.xlo2 = r.xhi2 = 0; r.ok = true;
+            __syncwarp();
+        } else {
+            r = pu_row<T>(g.alpha, p, K, false);
+        }
+        const unsigned gv0 = (unsigned)(g.base / VEC);                // SHORT: flat index of the chunk's first vector
+        auto row_of = [&](int v) { return pu_row_unpack<T>(rows_s[pu_row_local(p, g.tr, gv0 + (unsigned)v)]); };
         const int nvec = g.nvec;
         const uint4 *sv = reinterpret_cast<const uint4 *>(pu_smem + (size_t)stage * kChunkMax);
         T *og = reinterpret_cast<T *>(p.out) + g.base;
         uint4 *ov = reinterpret_cast<uint4 *>(og);
         antq_mbar_wait(full + stage, (phases >> slot) & 1u);
         phases ^= 1u << slot;
-        unsigned redo = 0;                                            // bit j: vector j * 32 + lane needs the exact pass
+        unsigned redo = 0, near = 0;                                  // bit j: vector j * 32 + lane is wild / near a midpoint
         if (r.ok && !(p.debug & 2)) {
             const uint4 *sp = sv + lane;
             uint4 *op = ov + lane;
@@ -373,68 +559,71 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
 #pragma unroll 1
             for (int v = lane; v + 32 < nvec; v += 64, j += 2) {
                 const uint4 r0 = sp[0], r1 = sp[32];
-                bool f0, f1;
-                const uint4 q0 = pu_vec<T, UNIFORM, XC>(r0, r, K, tab, f0);
-                const uint4 q1 = pu_vec<T, UNIFORM, XC>(r1, r, K, tab, f1);
+                bool n0, n1, w0, w1;
+                uint4 q0, q1;
+                if constexpr (SHORT) {
+                    q0 = pu_vec<T, UNIFORM, XC, true>(r0, row_of(v), K, tab, n0, w0);
+                    q1 = pu_vec<T, UNIFORM, XC, true>(r1, row_of(v + 32), K, tab, n1, w1);
+                } else {
+                    q0 = pu_vec<T, UNIFORM, XC, true>(r0, r, K, tab, n0, w0);
+                    q1 = pu_vec<T, UNIFORM, XC, true>(r1, r, K, tab, n1, w1);
+                }
                 antq_stg_stream(op, q0);
                 antq_stg_stream(op + 32, q1);
-                redo |= (f0 ? 1u : 0u) << j;
-                redo |= (f1 ? 2u : 0u) << j;
+                redo |= ((w0 ? 1u : 0u) | (w1 ? 2u : 0u)) << j;
+                near |= ((n0 ? 1u : 0u) | (n1 ? 2u : 0u)) << j;
                 sp += 64; op += 64;
             }
             if (j * 32 + lane < nvec) {
-                bool f0;
-                const uint4 q0 = pu_vec<T, UNIFORM, XC>(*sp, r, K, tab, f0);
+                bool n0, w0;
+                const uint4 q0 = SHORT ? pu_vec<T, UNIFORM, XC, true>(*sp, row_of(j * 32 + lane), K, tab, n0, w0)
+                                       : pu_vec<T, UNIFORM, XC, true>(*sp, r, K, tab, n0, w0);
                 antq_stg_stream(op, q0);
-                redo |= (f0 ? 1u : 0u) << j;
+                redo |= (w0 ? 1u : 0u) << j;
+                near |= (n0 ? 1u : 0u) << j;
+            }
+            // Near-midpoint vectors are NOT settled here: whatever a warp does after its last chunk is paid in full by
+            // the whole launch (the launch ends with its slowest warp), and the exact pass is ~0.3 us of dependent
+            // code per vector and lane.  They are parked in a CTA-wide queue (input vector, destination, row constants)
+            // and settled by all 512 threads at once after the last chunk.  A vector that is also wild is settled now,
+            // before the literal pass rewrites its wild elements.
+            if (!(p.debug & 4)) {
+                while (near) {
+                    const int jj = __ffs(near) - 1;
+                    near &= near - 1;
+                    const int v = jj * 32 + lane;
+                    float vs = r.s, vkx = r.kx;
+                    if constexpr (SHORT) { const PuRow rv = row_of(v); vs = rv.s; vkx = rv.kx; }
+                    const unsigned slot_q = ((redo >> jj) & 1u) ? kQCap : atomicAdd(qcount, 1u);
+                    if (slot_q < kQCap) {
+                        PuQEntry qe;
+                        qe.raw = sv[v]; qe.v = g.base / VEC + v; qe.s = vs; qe.kx = vkx;
+                        queue[slot_q] = qe;
+                    } else {
+                        antq_stg_stream(ov + v, pu_vec_exact<T, UNIFORM>(sv[v], vs, vkx, K, tab));
+                    }
+                }
             }
         } else if (p.debug & 2) {
             for (int v = lane; v < nvec; v += 32) antq_stg_stream(ov + v, sv[v]);
         } else {
             redo = 0xffffffffu;                                       // bad scale: every vector, literally
         }
-        if (__any_sync(0xffffffffu, redo != 0)) {
-            // Exact redo, dense: the flagged ELEMENTS of the whole chunk are compacted into a per-warp list and redone
-            // one per lane (a row with representable ties can flag a few percent of a chunk; redoing them vector by
-            // vector inside their owner lane serialised a warp for tens of microseconds: profiles/r02_notes.md).
-            unsigned long long em = 0;                                // bit 8 j + e: element e of vector j * 32 + lane
-            if (r.ok) {
-                for (int j = 0; j * 32 + lane < nvec; j++)
-                    if ((redo >> j) & 1u)
-                        em |= (unsigned long long)pu_vec_mask<T, UNIFORM>(sv[j * 32 + lane], r, K, tab) << (8 * j);
-            }
-            const int cnt = __popcll(em);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const bool overflow = !r.ok || total > kListMax;
-            if (!overflow) {
-                int pos = incl - cnt;
-                while (em) {
-                    const int b = __ffsll((long long)em) - 1;
-                    em &= em - 1;
-                    redo_list[pos++] = (unsigned short)((lane << 6) | b);
-                }
-                __syncwarp();          // list complete; the fast path's vector stores are ordered before the rewrites
-                for (int i = lane; i < total; i += 32) {
-                    const unsigned it = redo_list[i];
-                    const int v = (int)((it & 63u) >> 3) * 32 + (int)(it >> 6), e = (int)(it & 7u);
-                    const float xf = A::to_f32(reinterpret_cast<const T *>(sv + v)[e]);
-                    og[(long long)v * VEC + e] = pu_exact_elem<T>(cb, X, xf, r.s);
-                }
-                __syncwarp();          // the list is rewritten by this warp's next chunk
-            } else {
-                for (int j = 0; j * 32 + lane < nvec; j++) {
-                    if ((redo >> j) & 1u) {
-                        const int v = j * 32 + lane;
-                        pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
-                    }
+        if constexpr (SHORT) {
+            // wild vectors (outside the exact window, NaN, Inf, rows with a bad scale): literally, by their owner lane
+            if (!(p.debug & 4)) {
+                while (redo) {
+                    const int jj = __ffs(redo) - 1;
+                    redo &= redo - 1;
+                    const int v = jj * 32 + lane;
+                    PuRow rv = row_of(v);
+                    if (sizeof(T) == 2) rv.xl = pu_row_xl(p, rv.s);
+                    pu_redo_vec<T, UNIFORM>(cb, X, sv[v], rv, K, tab, og + (long long)v * VEC);
                 }
             }
+        } else {
+            if (__any_sync(0xffffffffu, redo != 0) && !(p.debug & 4))
+                pu_redo_chunk<T, UNIFORM>(cb, X, sv, og, nvec, r, K, tab, redo, redo_list, lane);
         }
         if (g.tail > 0 && lane == 0) {                                 // ragged tail of a per-tensor view
             const T *xg = reinterpret_cast<const T *>(p.x) + g.base + (long long)nvec * VEC;
@@ -445,19 +634,48 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
         k = kn;
         slot ^= 1;
     }
+    __syncthreads();
+    {
+        const unsigned nq = min(*qcount, (unsigned)kQCap);
+        // one thread per ELEMENT (the latency of this pass is added to the launch): 2- or 4-byte stores, ordered after
+        // the owners' vector stores by the barrier above
+        T *oute = reinterpret_cast<T *>(p.out);
+        for (unsigned i = threadIdx.x; i < nq * VEC; i += kThreads) {
+            const PuQEntry *qe = queue + i / VEC;
+            const unsigned e = i % VEC;
+            const float xf = A::to_f32(reinterpret_cast<const T *>(&qe->raw)[e]);
+            oute[qe->v * VEC + e] = A::from_f32_rn(pu_elem_exact<UNIFORM>(xf, qe->s, qe->kx, K, tab));
+        }
+    }
 }
 
 // ==================================================================================================
-// Short rows / scale groups: grid-stride over 16-byte vectors.
+// Short rows / scale groups.  A warp owns a tile of kTileVec consecutive 16-byte vectors (2 KiB):
+//   * all of the tile's loads are issued first (VPL vectors in flight per lane: a grid-stride loop with one vector
+//     per lane in flight was read-latency-bound, profiles/r02_notes.md);
+//   * the rows the tile touches have their constants (scale, reciprocal, window and clamp bounds: ~30 instructions
+//     with one IEEE division) computed ONCE, one row per lane, and parked in shared memory as one 16-byte word;
+//     each vector then fetches its row's constants with one LDS.128 instead of recomputing them.
 // ==================================================================================================
 constexpr int kShortThreads = 256;
+constexpr int kShortWarps = kShortThreads / 32;
+#ifndef ANTQ_PU_SHORT_VPL
+#define ANTQ_PU_SHORT_VPL 4
+#endif
+#ifndef ANTQ_PU_SHORT_CTAS
+#define ANTQ_PU_SHORT_CTAS 4
+#endif
+constexpr int kVPL = ANTQ_PU_SHORT_VPL;                     // vectors per lane per tile
+constexpr int kShortCtas = ANTQ_PU_SHORT_CTAS;              // resident CTAs per SM
+constexpr int kTileVec = 32 * kVPL;
 
 template <typename T, bool UNIFORM, bool XC>
-__global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const PuParams p) {
+__global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kernel(const PuParams p) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
     __shared__ float2 tab[UNIFORM ? 1 : 512];
     __shared__ float x_thr[ANTQ_MAX_GRID], x_lev[ANTQ_MAX_GRID];
+    __shared__ uint4 rows_s[kShortWarps][kTileVec];
     if (!UNIFORM) {
         for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
     }
@@ -469,17 +687,40 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_short_kernel(const P
     const PuK K = pu_load_k(p.cb);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < p.nvec; v += stride) {
-        const uint4 raw = antq_ldg_stream(xin + v);
-        unsigned row = 0;
-        if (p.alpha_per_row) row = p.cols_shift >= 0 ? v >> p.cols_shift : v / p.cols_vec;
-        const PuRow r = pu_row<T>(__ldg(p.alpha + row), p, K, true);
-        bool flag = true;
-        uint4 q = raw;
-        if (r.ok) q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, flag);
-        antq_stg_stream(xout + v, q);
-        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4 *rs = rows_s[warp];
+    const unsigned ntiles = (p.nvec + kTileVec - 1) / kTileVec;
+    const unsigned nwarps = gridDim.x * kShortWarps;
+    for (unsigned t = blockIdx.x * kShortWarps + warp; t < ntiles; t += nwarps) {
+        const unsigned v0 = t * kTileVec;
+        const unsigned vend = min(v0 + kTileVec, p.nvec);             // exclusive
+        uint4 raw[kVPL];
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            raw[j] = make_uint4(0, 0, 0, 0);
+            if (v < vend) raw[j] = antq_ldg_stream(xin + v);
+        }
+        const PuTileRows tr = pu_tile_rows(p, v0, vend - 1);
+        for (unsigned i = lane; i < tr.nrows; i += 32)
+            rs[i] = pu_row_pack<T>(pu_row<T>(__ldg(p.alpha + (p.alpha_per_row ? tr.row0 + i : 0u)), p, K, true));
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            if (v < vend) {
+                PuRow r = pu_row_unpack<T>(rs[pu_row_local(p, tr, v)]);
+                bool near, wild;
+                uint4 q = pu_vec<T, UNIFORM, XC>(raw[j], r, K, tab, near, wild);
+                if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
+                antq_stg_stream(xout + v, q);
+                if (wild) {
+                    if (sizeof(T) == 2) r.xl = pu_row_xl(p, r.s);
+                    pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+                }
+            }
+        }
+        __syncwarp();                                                 // rs is rewritten by this warp's next tile
     }
 }
 
@@ -528,17 +769,21 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const
         if (!live) continue;
         if (alpha_out && (v & (L - 1)) == 0) alpha_out[v >> p.cols_shift] = alpha;
         const PuRow r = pu_row<T>(alpha, p, K, true);
-        bool flag = true;
+        bool near = false, wild = true;
         uint4 q = raw;
-        if (r.ok) q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, flag);
+        if (r.ok) {
+            q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, near, wild);
+            if (near) q = pu_vec_exact<T, UNIFORM>(raw, r.s, r.kx, K, tab);
+        }
         antq_stg_stream(xout + v, q);
-        if (flag) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+        if (wild) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
     }
 }
 
-template <typename T, bool UNIFORM, bool XC> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
-    auto kernel = antq_pu_stream_kernel<T, UNIFORM, XC>;
-    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kNC * kListMax * 2;
+template <typename T, bool UNIFORM, bool XC, bool SHORT> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
+    auto kernel = antq_pu_stream_kernel<T, UNIFORM, XC, SHORT>;
+    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kQCap * (int)sizeof(PuQEntry) + kNC * kListMax * 2 +
+                     (SHORT ? kNC * kRowsPerChunk * 16 : 0);
     static unsigned long long configured = 0ull;                     // one bit per device ordinal
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -564,8 +809,9 @@ template <typename T, bool UNIFORM, bool XC> int launch_stream(const PuParams &p
 }
 
 template <typename T, bool UNIFORM, bool XC> int launch_short(const PuParams &p, cudaStream_t st) {
-    const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
-    const long long cap = (long long)antq_num_sms() * 8;
+    const long long tiles = ((long long)p.nvec + kTileVec - 1) / kTileVec;
+    const long long want = (tiles + kShortWarps - 1) / kShortWarps;
+    const long long cap = (long long)antq_num_sms() * kShortCtas;    // resident CTAs per SM (__launch_bounds__)
     antq_pu_short_kernel<T, UNIFORM, XC><<<(int)(want < cap ? want : cap), kShortThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
@@ -613,7 +859,7 @@ int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alph
     p.chunks_rem = p.total_chunks % (unsigned)ctas;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
     const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
-#define ANTQ_PU_GO(T, X) (uni ? launch_stream<T, true, X>(p, ctas, st) : launch_stream<T, false, X>(p, ctas, st))
+#define ANTQ_PU_GO(T, X) (uni ? launch_stream<T, true, X, false>(p, ctas, st) : launch_stream<T, false, X, false>(p, ctas, st))
     switch (dtype) {
         case ANTQ_F32: return ANTQ_PU_GO(float, false);
         case ANTQ_F16: return xc ? ANTQ_PU_GO(__half, true) : ANTQ_PU_GO(__half, false);
@@ -630,11 +876,15 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     const long long n = rows * cols;
     if (n == 0) return 0;
     if (cols % vec || (n / vec) > 0x7fffffffLL) return ANTQ_ENOTSUP;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("ANTQ_DEBUG"); dbg = e ? atoi(e) : 0; }
     PuParams p = {};
     p.x = x; p.out = out; p.alpha = alpha; p.cb = cb;
     p.rows = rows; p.cols = cols;
     p.nvec = (unsigned)(n / vec);
     p.cols_vec = (unsigned)(cols / vec);
+    if (p.cols_vec > 127u) return ANTQ_ENOTSUP;                       // pu_row_local's 16-bit reciprocal
+    p.cols_magic = 65536u / p.cols_vec + 1u;
     p.cols_shift = -1;
     if ((p.cols_vec & (p.cols_vec - 1)) == 0) {
         int sh = 0;
@@ -643,8 +893,32 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     }
     p.alpha_per_row = alpha_per_row;
     p.gmax = info->gmax; p.lim = info->lim;
+    p.debug = dbg;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
     const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
+    // Rows of 16 vectors and more (group-128 fp16 ...): the persistent TMA-staged kernel over the flat tensor (SHORT mode:
+    // 16.5-16.8 us per 4096^2 fp16 against 17.2-19 for the tile kernel).  Shorter rows: the tile kernel (group-32: 17 against
+    // 18.5-20: one row-table entry per 4 vectors is too much bookkeeping for the persistent kernel's single CTA per SM).
+    if (p.cols_vec >= 16) {
+        int chunk_bytes = kChunkMax;
+        const long long want = (long long)antq_num_sms() * kNC * 2;
+        while (chunk_bytes > 1024 && ((long long)p.nvec * 16 + chunk_bytes - 1) / chunk_bytes < want) chunk_bytes >>= 1;
+        p.chunk_elems = chunk_bytes / es;
+        p.chunks_per_row = 1; p.cpr_shift = 0;
+        p.total_chunks = (unsigned)(((long long)p.nvec * 16 + chunk_bytes - 1) / chunk_bytes);
+        const unsigned sms = (unsigned)antq_num_sms();
+        const int ctas = (int)(p.total_chunks < sms ? p.total_chunks : sms);
+        p.chunks_per_cta = p.total_chunks / (unsigned)ctas;
+        p.chunks_rem = p.total_chunks % (unsigned)ctas;
+#define ANTQ_PU_GO(T, X) (uni ? launch_stream<T, true, X, true>(p, ctas, st) : launch_stream<T, false, X, true>(p, ctas, st))
+        switch (dtype) {
+            case ANTQ_F32: return ANTQ_PU_GO(float, false);
+            case ANTQ_F16: return xc ? ANTQ_PU_GO(__half, true) : ANTQ_PU_GO(__half, false);
+            case ANTQ_BF16: return xc ? ANTQ_PU_GO(__nv_bfloat16, true) : ANTQ_PU_GO(__nv_bfloat16, false);
+        }
+#undef ANTQ_PU_GO
+        return ANTQ_EINVAL;
+    }
 #define ANTQ_PU_GO(T, X) (uni ? launch_short<T, true, X>(p, st) : launch_short<T, false, X>(p, st))
     switch (dtype) {
         case ANTQ_F32: return ANTQ_PU_GO(float, false);

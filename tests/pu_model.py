@@ -9,9 +9,12 @@ uniform progression with a power-of-two step 2^(e - mb_e).  So the nearest level
     t  = x * kx                    kx ~ 1 / (s c), a few ulps off
     mf = (t + M_e) - M_e           M_e = 1.5 * 2^23 * step_e : round t to a multiple of step_e (the octave's magic)
     q  = fl32(clamp(mf, kmin, kmax) * c);   out = fl32(q * s)        (STE is exact inside the window)
-and the result is provably the reference's unless t lies within delta_e of a midpoint (then the element is redone
-with the literal arithmetic: true division + exact thresholds).  delta_e = 2^(e - 19) covers the error of t
-(<= 5 ulp), of the levels (1 ulp) and of the scan's rounded distances (1-2 ulp) with margin.
+and the result is provably the reference's unless t lies within delta_e of a midpoint.  delta_e = 2^(e - 19) covers
+the error of t (<= 5 ulp), of the levels (1 ulp) and of the scan's rounded distances (1-2 ulp) with margin.  Such an
+element is settled without a search (pu_vec_exact): the winner is mf or its neighbour on t's side, mf +- step_e, and
+which one is the scan's own comparison of the two rounded distances on d = x / s, the upper level winning a tie
+(the grid is scanned in ascending order).  Only elements outside the window (|d| beyond the STE-exact range, NaN,
+Inf, dead rows) take the literal arithmetic.
 """
 import numpy as np
 
@@ -87,7 +90,7 @@ def _rz16(v):
     return h
 
 
-def forward(x, s, pu, lim, exact, out_dtype, xclamp=False):
+def forward(x, s, pu, lim, exact, out_dtype, xclamp=False, pair_all=False):
     """x: array of out_dtype; s: fp32 scale (alpha / max(grid)); lim: the codebook's exact window in d-space.
     `exact(xs)` is the literal reference arithmetic for the flagged elements.  Returns (out, flagged).
     xclamp (fp16 inputs, grids with pu["xc16"]): the clamp to [kmin, kmax] is applied to the INPUT with bounds rounded
@@ -118,10 +121,25 @@ def forward(x, s, pu, lim, exact, out_dtype, xclamp=False):
         xl = f32(f32(f32(lim) * s) * f32(0.9990234375))
         window = np.abs(xf) <= xl                                 # False for NaN
         row_ok = bool(s > 0) and bool(np.isfinite(s)) and bool(np.isfinite(kx)) and bool(kx > 0)
-    flagged = near | ~window
+        # pu_vec_exact: the pair decision, from the UNCLAMPED input
+        tp = (xf * kx).astype(f32)
+        Mp = pu["magic"][(_bits(tp) >> 23) & 0xff]
+        step = ((_bits(Mp) & np.uint32(0x7f800000)) - np.uint32(23 << 23)).view(f32)
+        mp = ((tp + Mp).astype(f32) - Mp).astype(f32)
+        rp = (tp - mp).astype(f32)
+        oth = (mp + np.copysign(step, rp)).astype(f32)
+        clip = lambda k: np.minimum(np.maximum(k, pu["kmin"]), pu["kmax"]).astype(f32)
+        k1, k2 = clip(mp), clip(oth)
+        ql, qh = (np.minimum(k1, k2) * pu["c"]).astype(f32), (np.maximum(k1, k2) * pu["c"]).astype(f32)
+        d = (xf / s).astype(f32)
+        pick = np.where(np.abs((d - qh).astype(f32)) <= np.abs((d - ql).astype(f32)), qh, ql).astype(f32)
+        opair = (((pick - d).astype(f32) + d).astype(f32) * s).astype(f32)
+    wild = ~window
     if not row_ok:
-        flagged = np.ones_like(flagged)
-    out = o.astype(out_dtype)
-    if flagged.any():
-        out[flagged] = exact(x[flagged])
-    return out, flagged
+        wild = np.ones_like(wild)
+    if pair_all:                                                  # test hook: the pair decision for EVERY in-window element
+        near = np.ones_like(near)
+    out = np.where(near, opair, o).astype(out_dtype)
+    if wild.any():
+        out[wild] = exact(x[wild])
+    return out, near | wild

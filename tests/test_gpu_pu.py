@@ -120,6 +120,36 @@ def test_pu_random(antq, kind, bit, signed, dtype):
     assert_bit_equal(to_np(xd), ref, "in place")
 
 
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("kind,bit,signed", [("int", 8, True), ("flint", 4, False), ("flint", 5, True)])
+def test_pu_short_rows_ragged_shapes(antq, kind, bit, signed, dtype):
+    """The tiled short-row kernel: row lengths that are not powers of two (rows straddle the 128-vector tiles, the row
+    of a vector comes from the 16-bit reciprocal), a partial last tile, the longest rows the plan sends there
+    (504 fp16 / 508 fp32 elements), one-vector rows, dead and NaN rows."""
+    rng = np.random.default_rng(5 + bit)
+    grid = orc.ant_grid(kind, bit, signed)
+    cb = _cb(antq, grid)
+    vec = 8 if dtype == "f16" else 4
+    for cols_vec, rows in ((1, 1031), (3, 517), (5, 77), (9, 333), (25, 41), (63, 19), (127 if vec == 4 else 62, 23), (4, 2), (2, 1)):
+        cols = cols_vec * vec
+        x = (rng.standard_normal((rows, cols)) * 0.02).astype(np.float32)
+        x[rng.integers(0, rows, 9), rng.integers(0, cols, 9)] *= 30
+        if rows > 12:
+            x[7] = 0.0
+            x[11, 0] = np.nan
+        if not signed:
+            x = np.abs(x)
+        if dtype == "f16":
+            x = x.astype(np.float16)
+        alpha = (np.abs(np.nan_to_num(x.astype(np.float32), nan=0)).max(1) * rng.uniform(0.5, 1.2, rows)).astype(np.float32)
+        alpha[::5] = np.float32(0.05 * grid.max() / 8)                    # representable ties
+        xt = torch.from_numpy(x).to(dev())
+        if rows > 1:
+            assert antq.fakequant_plan(xt, cb, True) == 5, (cols_vec, rows)
+        ref = orc.ant_forward(x, alpha, grid, per_row=True)
+        assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, 0)), ref, "short rows %d x %d" % (rows, cols))
+
+
 def test_default_plans(antq):
     """What a model actually hits: 8-bit int weights and post-ReLU 4-bit activations take the closed form, signed 4-bit
     keeps the chain, OliVe keeps its two-phase chain."""

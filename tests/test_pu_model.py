@@ -68,6 +68,10 @@ def test_fp16_exhaustive(kind, bit, signed):
             got2, _ = pm.forward(ALL_F16, s_eff, pu, lim_of(cb), exact, np.float16, xclamp=True)
             same = (got2.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got2) & np.isnan(ref))
             assert same.all(), ("xclamp", kind, bit, signed, s, ALL_F16[~same][:5], got2[~same][:5], ref[~same][:5])
+        # the pair decision that settles near-midpoint elements must equal the scan for EVERY in-window element
+        got3, _ = pm.forward(ALL_F16, s_eff, pu, lim_of(cb), exact, np.float16, pair_all=True)
+        same = (got3.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got3) & np.isnan(ref))
+        assert same.all(), ("pair", kind, bit, signed, s, ALL_F16[~same][:5], got3[~same][:5], ref[~same][:5])
         inwin = np.abs(ALL_F16.astype(f32)) <= f32(lim_of(cb) * s_eff) * f32(0.99)
         flagged += (fl & inwin).sum() / max(inwin.sum(), 1)
     assert flagged / len(scales(gmax, 6 if bit >= 7 else 10)) < 0.02          # the closed form is what runs
@@ -95,6 +99,9 @@ def test_fp32_threshold_huggers(kind, bit, signed):
         ref = orc.ant_forward(x, alpha, grid, per_row=False)
         same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
         assert same.all(), (kind, s, x[~same][:5], got[~same][:5], ref[~same][:5])
+        got3, _ = pm.forward(x, s_eff, pu, lim_of(cb), exact, f32, pair_all=True)
+        same = (got3.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got3) & np.isnan(ref))
+        assert same.all(), ("pair", kind, s, x[~same][:5], got3[~same][:5], ref[~same][:5])
         # WITHOUT the near-midpoint redo the closed form would be wrong somewhere among the huggers -> the test bites
     # sanity: the model really is exercised on its own (few flagged among the random part)
     assert fl[:30000].mean() < 0.01
