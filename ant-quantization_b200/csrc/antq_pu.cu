@@ -730,11 +730,12 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
 // reduction (integer max on the fp32 bit patterns of |x|: NaN-propagating, like torch's abs().max()), then the closed form.
 // ==================================================================================================
 template <typename T, bool UNIFORM, bool XC>
-__global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const PuParams p, float ratio, float *__restrict__ alpha_out) {
+__global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_kernel(const PuParams p, float ratio, float *__restrict__ alpha_out) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
     __shared__ float2 tab[UNIFORM ? 1 : 512];
     __shared__ float x_thr[ANTQ_MAX_GRID], x_lev[ANTQ_MAX_GRID];
+    __shared__ uint4 rows_s[kShortWarps][kTileVec];
     if (!UNIFORM) {
         for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
     }
@@ -746,37 +747,74 @@ __global__ void __launch_bounds__(kShortThreads, 4) antq_pu_dynamic_kernel(const
     const PuK K = pu_load_k(p.cb);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
-    const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned L = p.cols_vec;                                    // lanes per group
-    const unsigned nvec_up = (p.nvec + 31u) & ~31u;                   // every lane of a warp runs the same trip count
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec_up; v += stride) {
-        const bool live = v < p.nvec;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (live) raw = antq_ldg_stream(xin + v);
-        T xv[VEC];
-        *reinterpret_cast<uint4 *>(xv) = raw;
-        unsigned m = 0;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4 *rs = rows_s[warp];
+    const unsigned L = p.cols_vec;                                    // lanes per group (a power of two <= 32)
+    const int sh = p.cols_shift;
+    const unsigned ntiles = (p.nvec + kTileVec - 1) / kTileVec;
+    const unsigned nwarps = gridDim.x * kShortWarps;
+    // Same tile structure as antq_pu_short_kernel: the tile's loads first, then one abs-max per group (xor shuffles over the
+    // group's L lanes), then the groups' constants ONCE, one group per lane (its alpha fetched from the lane that holds the
+    // group's first vector), parked in shared memory for the group's vectors.
+    for (unsigned t = blockIdx.x * kShortWarps + warp; t < ntiles; t += nwarps) {
+        const unsigned v0 = t * kTileVec;
+        const unsigned vend = min(v0 + kTileVec, p.nvec);             // exclusive; a multiple of L (whole groups)
+        uint4 raw[kVPL];
+        float am[kVPL];
 #pragma unroll
-        for (int e = 0; e < VEC; e++) {
-            const unsigned b = __float_as_uint(A::to_f32(xv[e])) & 0x7fffffffu;
-            m = b > m ? b : m;
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            raw[j] = make_uint4(0, 0, 0, 0);
+            if (v < vend) raw[j] = antq_ldg_stream(xin + v);
         }
-        for (unsigned o = 1; o < L; o <<= 1) {
-            const unsigned t = __shfl_xor_sync(0xffffffffu, m, o);
-            m = t > m ? t : m;
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            T xv[VEC];
+            *reinterpret_cast<uint4 *>(xv) = raw[j];
+            unsigned m = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const unsigned b = __float_as_uint(A::to_f32(xv[e])) & 0x7fffffffu;
+                m = b > m ? b : m;
+            }
+            for (unsigned o = 1; o < L; o <<= 1) {
+                const unsigned u = __shfl_xor_sync(0xffffffffu, m, o);
+                m = u > m ? u : m;
+            }
+            am[j] = __fmul_rn(__uint_as_float(m), ratio);             // alpha = absmax * ratio (fp32, like the torch expression)
         }
-        const float alpha = __fmul_rn(__uint_as_float(m), ratio);     // alpha = absmax * ratio (fp32, like the torch expression)
-        if (!live) continue;
-        if (alpha_out && (v & (L - 1)) == 0) alpha_out[v >> p.cols_shift] = alpha;
-        const PuRow r = pu_row<T>(alpha, p, K, true);
-        bool near = false, wild = true;
-        uint4 q = raw;
-        if (r.ok) {
-            q = pu_vec<T, UNIFORM, XC>(raw, r, K, tab, near, wild);
-            if (near) q = pu_vec_exact<T, UNIFORM>(raw, r.s, r.kx, K, tab);
+        const unsigned row0 = v0 >> sh, nrows = (vend - v0) >> sh;    // groups of this tile: <= kTileVec / L
+        for (unsigned k = 0; k * 32u < nrows; k++) {
+            const unsigned r = k * 32u + lane;                        // group r of the tile starts at vector r * L
+            const unsigned src = (r << sh) & 31u, jsrc = (r << sh) >> 5;
+            float al = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kVPL; j++) {
+                const float g = __shfl_sync(0xffffffffu, am[j], src);
+                al = jsrc == (unsigned)j ? g : al;
+            }
+            if (r < nrows) {
+                rs[r] = pu_row_pack<T>(pu_row<T>(al, p, K, true));
+                if (alpha_out) alpha_out[row0 + r] = al;
+            }
         }
-        antq_stg_stream(xout + v, q);
-        if (wild) pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            if (v < vend) {
+                PuRow r = pu_row_unpack<T>(rs[(v - v0) >> sh]);
+                bool near, wild;
+                uint4 q = pu_vec<T, UNIFORM, XC>(raw[j], r, K, tab, near, wild);
+                if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
+                antq_stg_stream(xout + v, q);
+                if (wild) {
+                    if (sizeof(T) == 2) r.xl = pu_row_xl(p, r.s);
+                    pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+                }
+            }
+        }
+        __syncwarp();                                                 // rs is rewritten by this warp's next tile
     }
 }
 
@@ -952,8 +990,9 @@ int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float rat
     p.alpha_per_row = 1;
     p.gmax = info->gmax; p.lim = info->lim;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
-    const long long want = ((long long)p.nvec + kShortThreads - 1) / kShortThreads;
-    const long long cap = (long long)antq_num_sms() * 8;
+    const long long tiles = ((long long)p.nvec + kTileVec - 1) / kTileVec;
+    const long long want = (tiles + kShortWarps - 1) / kShortWarps;
+    const long long cap = (long long)antq_num_sms() * kShortCtas;
     const int ctas = (int)(want < cap ? want : cap);
     const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
 #define ANTQ_PU_GO(T, X)                                                                                      \

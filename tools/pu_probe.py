@@ -33,10 +33,15 @@ for kind, bit, signed in (("int", 8, True), ("flint", 4, False), ("int", 6, True
     for gsz in (8, 16, 32, 64, 128, 256):
         a_g = [(x.view(-1, gsz).float().abs().amax(1) * 0.9).contiguous() for x in xs]
         out[key]["g%%d" %% gsz] = run(lambda t: t.view(-1, gsz), a_g, True)
+    for gsz in (8, 32, 128):
+        def stepd():
+            for i in range(len(xs)):
+                antq.fakequant_dynamic(xs[i].view(-1), cb, gsz, ratio=0.9, out=outs[i].view(-1))
+        out[key]["dyn%%d" %% gsz] = round(time_graph(stepd, 20) / len(xs), 2)
 print(json.dumps(out))
 ''' % (ROOT, ROOT)
 
-for suffix, dbg in (("", "0"), ("", "4")):
+for suffix, dbg in (("", "0"),):
     env = dict(os.environ, ANTQ_LIB_SUFFIX=suffix, ANTQ_DEBUG=dbg)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]

@@ -101,7 +101,7 @@ def main():
              ("flint", 4, False, False), ("int", 4, False, False), ("int", 8, True, False), ("int", 8, False, False),
              ("int", 6, True, False), ("flint", 6, False, False), ("flint", 5, True, False),
              ("int", 4, True, True), ("flint", 4, True, True), ("flint", 4, False, True)]
-    grans = ["tensor", "row", "g8", "g16", "g32"]
+    grans = ["tensor", "row", "g8", "g16", "g32", "g128"]
     rows = []
     with open(a.out, "w") as f:
         def emit(r):
