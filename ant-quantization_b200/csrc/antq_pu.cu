@@ -934,10 +934,11 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     p.debug = dbg;
     const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
     const bool xc = dtype == ANTQ_F16 ? (info->flags & ANTQ_CB_PU_XC16) != 0 : dtype == ANTQ_BF16 ? (info->flags & ANTQ_CB_PU_XCBF) != 0 : false;
-    // Rows of 16 vectors and more (group-128 fp16 ...): the persistent TMA-staged kernel over the flat tensor (SHORT mode:
-    // 16.5-16.8 us per 4096^2 fp16 against 17.2-19 for the tile kernel).  Shorter rows: the tile kernel (group-32: 17 against
-    // 18.5-20: one row-table entry per 4 vectors is too much bookkeeping for the persistent kernel's single CTA per SM).
-    if (p.cols_vec >= 16) {
+    // Uniform grids (int-k), rows of 16 vectors and more (group-128 fp16 ...): the persistent TMA-staged kernel over the flat
+    // tensor (SHORT mode: 16.4-16.8 us per 4096^2 fp16 against 17.2-19 for the tile kernel).  Shorter rows, and the
+    // per-octave-table grids at any length (20.1 against 18.4-19): the tile kernel -- one row-table entry per few vectors is
+    // too much bookkeeping for the persistent kernel's single CTA per SM.
+    if (p.cols_vec >= 16 && uni) {
         int chunk_bytes = kChunkMax;
         const long long want = (long long)antq_num_sms() * kNC * 2;
         while (chunk_bytes > 1024 && ((long long)p.nvec * 16 + chunk_bytes - 1) / chunk_bytes < want) chunk_bytes >>= 1;

@@ -109,9 +109,9 @@ def main():
     write("r02_stream_sass.txt", d + " (headline: signed 4-bit chain)",
           ["cp.async.bulk -> UBLKCP; mbarrier -> SYNCS.*; threshold chain = HSET2 / HFMA2 (two pipes) + LOP3"], l, "HSET2")
     for needles, name, note in (
-            (("antq_pu_stream_kernel<__half, (bool)1, (bool)1>",), "r02_pu_sass.txt",
+            (("antq_pu_stream_kernel<__half, (bool)1, (bool)1, (bool)0>",), "r02_pu_sass.txt",
              "closed form, uniform grid (int-k), x-space clamp on packed halves (HMNMX2)"),
-            (("antq_pu_stream_kernel<__half, (bool)0, (bool)1>",), "r02_pu_table_sass.txt",
+            (("antq_pu_stream_kernel<__half, (bool)0, (bool)1, (bool)0>",), "r02_pu_table_sass.txt",
              "closed form, per-octave table (flint / pot / float), x-space clamp")):
         d, l = pick(fns, *needles)
         write(name, d, [note, "per element: cvt (HADD2.F32), FMUL kx, FADD +M, FADD -M, FADD diff, FFMA/FSETP flag, FMUL *c*s ... F2FP pack"], l, "FADD")
