@@ -13,7 +13,7 @@ int antq_launch_short(const void *x, void *out, const float *alpha, int alpha_pe
                       int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
 int antq_short_thresholds(const antq_codebook_info *info, bool ovp);
 int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
-                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st);
 int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st);
 int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float ratio, long long rows, long long cols, int dtype,
@@ -90,7 +90,10 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
     const bool exact = info && (info->flags & ANTQ_CB_WELLSEP) && (info->flags & ANTQ_CB_STE_EXACT) && aligned && !codes;
     // closed form (antq_pu.cu): any piecewise-uniform grid, no OVP
-    const bool pu = exact && (info->flags & ANTQ_CB_PU) && !ovp && !(flags & ANTQ_FLAG_NO_PU);
+    // ... or, with outlier-victim pairs, a codebook whose NORMAL levels are (ANTQ_CB_PU_OVP): whole vectors, pairs inside rows
+    const bool pu = exact && !(flags & ANTQ_FLAG_NO_PU) &&
+                    (ovp ? (info->flags & ANTQ_CB_PU_OVP) && (info->flags & ANTQ_CB_OVP_OK) && cols % vec == 0
+                         : (info->flags & ANTQ_CB_PU) != 0);
     const bool long_rows = (cols >= kRowsMinCols || (flags & ANTQ_FLAG_FORCE_ROWS)) && (cols % vec == 0 || rows == 1);
     bool chain = false;
     int nt = 0;
@@ -104,18 +107,20 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     if (flags & ANTQ_FLAG_FORCE_ROWS) return chain ? 1 : ANTQ_ENOTSUP;
     if (flags & ANTQ_FLAG_FORCE_PU) {
         if (pu && long_rows) return 4;
-        if (pu && rows > 1 && cols % vec == 0) return 5;
+        if (pu && !ovp && rows > 1 && cols % vec == 0) return 5;
         return ANTQ_ENOTSUP;
     }
     // the compare chain (packed 16-bit arithmetic, two elements per instruction) wins while it is short: <= 7 thresholds
     // after folding signs = every signed 4-bit grid and OliVe's two-phase chain (13.7-15 us per 4096^2 fp16).  Beyond
     // that the closed form does (fp32 per element but independent of the number of levels, 17-20 us): unsigned 4-bit,
     // 5 to 8 bit.  Measured side by side in profiles/r02_notes.md.
-    if (chain && (nt <= 7 || !pu)) return 1;
+    // (OliVe's signed 4-bit codebooks keep the two-phase chain: 7 thresholds in phase one, 13.2-15.1 us)
+    const bool ovp2_fast = ovp && info && (info->flags & ANTQ_CB_SYMMETRIC) && nt <= 15;
+    if (chain && (nt <= 7 || !pu || ovp2_fast)) return 1;
     if (pu && long_rows) return 4;
     if (chain) return 1;
     const bool short_rows = info && !codes && aligned && rows > 1 && cols < kRowsMinCols && cols % vec == 0;
-    if (short_rows && pu) return 5;
+    if (short_rows && pu && !ovp) return 5;
     // short rows / scale groups of the other grids: the d-space chain kernel (<= 15 thresholds after folding signs)
     if (short_rows && (info->flags & ANTQ_CB_WELLSEP) && antq_short_thresholds(info, ovp) >= 1 &&
         antq_short_thresholds(info, ovp) <= 15 && (!ovp || (info->flags & ANTQ_CB_OVP_OK)))
@@ -141,7 +146,7 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
     switch (plan) {
         case 1: rc = antq_launch_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp, st); break;
         case 3: rc = antq_launch_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp, st); break;
-        case 4: rc = antq_launch_pu_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, st); break;
+        case 4: rc = antq_launch_pu_stream(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, ovp, st); break;
         case 5: rc = antq_launch_pu_short(x, out, alpha, alpha_per_row, rows, cols, dtype, cb, info, st); break;
         default: break;
     }

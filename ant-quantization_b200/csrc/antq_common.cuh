@@ -41,6 +41,7 @@ struct AntqCodebook {
     // ANTQ_CB_PU (piecewise-uniform closed form, antq_pu.cu): every level is fl32(k * pu_c) for an integer k in
     // [pu_kmin, pu_kmax], and inside each octave of |k| the k's form a progression with a power-of-two step.
     float pu_c, pu_inv_c, pu_kmin, pu_kmax;
+    float pu_tout;       // ANTQ_CB_PU_OVP: |d| < pu_tout never reaches an outlier level (else +inf)
     float2 pu_tab[256];                 // by biased exponent of t = d / pu_c: {1.5 * 2^23 * step, near-midpoint delta}
 };
 

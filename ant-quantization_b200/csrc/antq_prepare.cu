@@ -220,7 +220,37 @@ __global__ void __launch_bounds__(ANTQ_MAX_GRID) antq_prepare_kernel(const float
         if (ovp_index < 0 && !sym) { /* no outlier level at all: OVP is a no-op */ }
         if (ovp_ok) flags |= ANTQ_CB_OVP_OK;
         cb->pu_c = 0.0f; cb->pu_inv_c = 0.0f; cb->pu_kmin = 0.0f; cb->pu_kmax = 0.0f;
+        cb->pu_tout = __int_as_float(0x7f800000);
         if (sep && ste) flags |= antq_pu_analyze(lev, lcode, L, keep, cb);     // keep[] is free by now: scratch
+        // OliVe: grid + outliers is not piecewise uniform, but the NORMAL levels (|v| <= 32, O/antquant/quant_modules.py:314)
+        // usually are.  Then every element with thr[lo - 1] <= d < thr[hi] quantizes inside the normal grid by the closed
+        // form, and only vectors holding an element beyond that window -- an outlier, which also makes its neighbour a
+        // victim -- need the pair logic on the whole codebook (antq_pu.cu, OVP mode).
+        // (The pu_* fields then describe the normal levels, so a whole-codebook ANTQ_CB_PU found above is withdrawn: launches
+        // without pairs on an OliVe codebook take the chain / generic kernels.)
+        if (sep && ste && k_out > 0 && ovp_ok) {
+            int lo = 0, hi = L - 1;
+            while (lo < L && fabsf(lev[lo]) > 32.0f) lo++;
+            while (hi >= 0 && fabsf(lev[hi]) > 32.0f) hi--;
+            bool contiguous = lo <= hi;
+            for (int r = lo; r <= hi && contiguous; r++)
+                if (fabsf(lev[r]) > 32.0f) contiguous = false;
+            if (contiguous && (lo > 0 || hi < L - 1)) {
+                const int whole = flags & (ANTQ_CB_PU | ANTQ_CB_PU_UNIFORM | ANTQ_CB_PU_XC16 | ANTQ_CB_PU_XCBF | ANTQ_CB_PU_E4M3);
+                const int sub = antq_pu_analyze(lev + lo, lcode + lo, hi - lo + 1, keep, cb);
+                flags &= ~whole;
+                if (!(sub & ANTQ_CB_PU) && whole) flags |= antq_pu_analyze(lev, lcode, L, keep, cb);   // restore the fields
+                if (sub & ANTQ_CB_PU) {
+                    float tout = __int_as_float(0x7f800000);
+                    if (hi < L - 1) tout = fminf(tout, thr[hi]);
+                    if (lo > 0) tout = fminf(tout, -thr[lo - 1]);
+                    if (tout > 0.0f) {
+                        cb->pu_tout = tout;
+                        flags |= ANTQ_CB_PU_OVP | (sub & ~(ANTQ_CB_PU | ANTQ_CB_PU_E4M3));
+                    }
+                }
+            }
+        }
 
         cb->n_entries = K;
         cb->n_normal = k_normal;

@@ -35,7 +35,8 @@ constexpr int kNC = ANTQ_PU_CONSUMERS;    // consumer warps per CTA
 constexpr int kNS = 2 * kNC;              // two private stages per warp
 constexpr int kChunkMax = 4096;
 constexpr int kThreads = kNC * 32;
-constexpr int kListMax = 512;             // per-warp work list of elements to redo exactly (per chunk)
+constexpr int kListMax = 1024;            // per-warp work list of elements / pairs to redo literally (per chunk; a chunk holds <= 1024 pairs)
+constexpr int kScratch = 2176;            // per-warp scratch in bytes: that list, or (SHORT) the chunk's row table
 constexpr int kQCap = 512;                // CTA-wide queue of near-midpoint vectors settled after the last chunk
 struct __align__(16) PuQEntry { uint4 raw; long long v; float s, kx; };
 
@@ -49,6 +50,7 @@ struct PuParams {
     int alpha_per_row, chunks_per_row, chunk_elems, cpr_shift;
     float gmax, lim;
     int debug;
+    int ovp;                                   // OliVe outlier-victim pairs (ANTQ_CB_PU_OVP codebooks)
     // short kernel
     unsigned nvec, cols_vec, cols_magic;
     int cols_shift;
@@ -58,9 +60,11 @@ struct PuK {                               // the codebook's closed-form constan
     float c, inv_c, kmin, kmax;
     float xc_lo, xc_hi;                    // x-space clamp: (kmin - 0.4 step_top) and (kmax + 0.4 step_top), in units of c
     float hd_c;                            // uniform grids behind the x-space clamp: 0.5 - (max|k| + 1) 2^-19, one constant
+    float lim;                             // |d| <= lim: the closed form is proven (OVP: and no outlier level is reached)
 };
-__device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb) {
+__device__ __forceinline__ PuK pu_load_k(const AntqCodebook *__restrict__ cb, const float lim, const int ovp) {
     PuK k;
+    k.lim = ovp ? fminf(lim, cb->pu_tout) : lim;
     k.c = cb->pu_c; k.inv_c = cb->pu_inv_c; k.kmin = cb->pu_kmin; k.kmax = cb->pu_kmax;
     // step of the octave each end of the grid lies in, from that octave's magic constant M = 1.5 * 2^23 * step
     // (kmin = 0: exponent field 0 -> the sub-unit region's entry)
@@ -89,7 +93,7 @@ __device__ __forceinline__ PuRow pu_row(float alpha, const PuParams &p, const Pu
     else rs = __fdiv_rn(1.0f, r.s);
     r.kx = __fmul_rn(rs, K.inv_c);
     r.ok = r.s > 0.0f && r.s < inf && r.kx > 0.0f && r.kx < inf;
-    r.xl = __fmul_rn(__fmul_rn(p.lim, r.s), 0.9990234375f);           // conservative exact window in x-space
+    r.xl = __fmul_rn(__fmul_rn(K.lim, r.s), 0.9990234375f);           // conservative exact window in x-space
     r.xl2 = 0; r.xlo2 = 0; r.xhi2 = 0;
     if constexpr (sizeof(T) == 2) {
         const uint32_t b = AntqType<T>::bits(AntqType<T>::from_f32_rz(r.xl));
@@ -197,6 +201,40 @@ template <> struct PuIO<__nv_bfloat16> {
         return q;
     }
 };
+
+// One element, literally, WITHOUT the rescale: the level the scan picks and the quotient it was picked for.
+__device__ __forceinline__ void pu_exact_qd(const AntqCodebook *__restrict__ cb, const PuExact &X, float xf, float s, float &q, float &d) {
+    d = __fdiv_rn(xf, s);
+    if (fabsf(d) <= X.win) {
+        q = X.lev[antq_rank(X.thr, X.nlev - 1, d)];
+    } else {
+        int code;
+        q = antq_scan_literal(cb->grid, cb->n_entries, d, code);
+    }
+}
+// OliVe outlier-victim pair (O/antquant/quant_modules.py:311-320): an outlier (|q| > 32) in the even slot zeroes the odd
+// one, else an outlier in the odd slot zeroes the even one; then STE and rescale, each with its own quotient.
+template <typename T>
+__device__ __forceinline__ void pu_exact_pair(const AntqCodebook *__restrict__ cb, const PuExact &X, float x0, float x1, float s,
+                                              T &o0, T &o1) {
+    float q0, d0, q1, d1;
+    pu_exact_qd(cb, X, x0, s, q0, d0);
+    pu_exact_qd(cb, X, x1, s, q1, d1);
+    const bool oe = fabsf(q0) > 32.0f, oo = fabsf(q1) > 32.0f;
+    if (oe) q1 = __fmul_rn(q1, 0.0f);
+    else if (oo) q0 = __fmul_rn(q0, 0.0f);
+    o0 = AntqType<T>::from_f32_rn(antq_ste_rescale(q0, d0, s));
+    o1 = AntqType<T>::from_f32_rn(antq_ste_rescale(q1, d1, s));
+}
+// A whole vector through the pair logic (queue overflow, rows with a bad scale).
+template <typename T>
+__device__ __noinline__ void pu_redo_vec_ovp(const AntqCodebook *__restrict__ cb, const PuExact X, const uint4 raw, const float s, T *og) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC];
+    PuIO<T>::unpack(raw, f);
+#pragma unroll
+    for (int e = 0; e < VEC; e += 2) pu_exact_pair<T>(cb, X, f[e], f[e + 1], s, og[e], og[e + 1]);
+}
 
 // One 16-byte vector through the closed form.  `near` = some element lies within delta of a midpoint (settled by
 // pu_vec_exact); `wild` = some element is outside the window in which the closed form is proven (|d| beyond the STE
@@ -308,14 +346,19 @@ __device__ __noinline__ void pu_redo_vec(const AntqCodebook *__restrict__ cb, co
 template <typename T, bool UNIFORM>
 __device__ __noinline__ void pu_redo_chunk(const AntqCodebook *__restrict__ cb, const PuExact X, const uint4 *sv, T *og,
                                            const int nvec, const PuRow r, const PuK K, const float2 *tab, const unsigned redo,
-                                           unsigned short *redo_list, const int lane) {
+                                           unsigned short *redo_list, const int lane, const bool ovp) {
     typedef AntqType<T> A;
     constexpr int VEC = A::kVec;
-    unsigned long long em = 0;                                        // bit 8 j + e: element e of vector j * 32 + lane
+    // bit 8 j + e: element e of vector j * 32 + lane.  OliVe pairs: a pair with a wild element is one work item, filed
+    // under its even element (its partner may become a victim, or be the outlier that makes it one).
+    unsigned long long em = 0;
     if (r.ok) {
         for (int j = 0; j * 32 + lane < nvec; j++)
-            if ((redo >> j) & 1u)
-                em |= (unsigned long long)pu_vec_mask<T, UNIFORM>(sv[j * 32 + lane], r, K, tab) << (8 * j);
+            if ((redo >> j) & 1u) {
+                unsigned m = pu_vec_mask<T, UNIFORM>(sv[j * 32 + lane], r, K, tab);
+                if (ovp) m = (m | (m >> 1)) & 0x55u;
+                em |= (unsigned long long)m << (8 * j);
+            }
     }
     const int cnt = __popcll(em);
     int incl = cnt;
@@ -337,15 +380,18 @@ __device__ __noinline__ void pu_redo_chunk(const AntqCodebook *__restrict__ cb, 
         for (int i = lane; i < total; i += 32) {
             const unsigned it = redo_list[i];
             const int v = (int)((it & 63u) >> 3) * 32 + (int)(it >> 6), e = (int)(it & 7u);
-            const float xf = A::to_f32(reinterpret_cast<const T *>(sv + v)[e]);
-            og[(long long)v * VEC + e] = pu_exact_elem<T>(cb, X, xf, r.s);
+            const T *xe = reinterpret_cast<const T *>(sv + v);
+            T *oe = og + (long long)v * VEC;
+            if (ovp) pu_exact_pair<T>(cb, X, A::to_f32(xe[e]), A::to_f32(xe[e + 1]), r.s, oe[e], oe[e + 1]);
+            else oe[e] = pu_exact_elem<T>(cb, X, A::to_f32(xe[e]), r.s);
         }
         __syncwarp();          // the list is rewritten by this warp's next chunk
     } else {
         for (int j = 0; j * 32 + lane < nvec; j++) {
             if ((redo >> j) & 1u) {
                 const int v = j * 32 + lane;
-                pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
+                if (ovp) pu_redo_vec_ovp<T>(cb, X, sv[v], r.s, og + (long long)v * VEC);
+                else pu_redo_vec<T, UNIFORM>(cb, X, sv[v], r, K, tab, og + (long long)v * VEC);
             }
         }
     }
@@ -387,8 +433,8 @@ template <typename T> __device__ __forceinline__ PuRow pu_row_unpack(const uint4
     }
     return r;
 }
-__device__ __forceinline__ float pu_row_xl(const PuParams &p, float s) {
-    return __fmul_rn(__fmul_rn(p.lim, s), 0.9990234375f);
+__device__ __forceinline__ float pu_row_xl(const PuK &K, float s) {
+    return __fmul_rn(__fmul_rn(K.lim, s), 0.9990234375f);
 }
 
 struct PuTileRows {                          // which rows a tile touches and how a vector finds its row
@@ -422,6 +468,7 @@ __device__ __forceinline__ unsigned pu_row_local(const PuParams &p, const PuTile
 // table, and every vector fetches its row's constants with one LDS.128.
 // ==================================================================================================
 constexpr int kRowsPerChunk = 132;        // 256 vectors / 2 per row + straddle, rounded up
+static_assert(kRowsPerChunk * 16 <= kScratch && kListMax * 2 <= kScratch, "per-warp scratch");
 template <typename T, bool UNIFORM, bool XC, bool SHORT>
 __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuParams p) {
     typedef AntqType<T> A;
@@ -434,9 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     unsigned *next_k = reinterpret_cast<unsigned *>(full + kNS);
     unsigned *qcount = next_k + 1;
     PuQEntry *queue = reinterpret_cast<PuQEntry *>(next_k + 4);
-    unsigned short *redo_list = reinterpret_cast<unsigned short *>(queue + kQCap) + (size_t)(threadIdx.x >> 5) * kListMax;
-    uint4 *rows_s = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned short *>(queue + kQCap) + (size_t)kNC * kListMax) +
-                    (size_t)(threadIdx.x >> 5) * kRowsPerChunk;       // SHORT only (not allocated otherwise)
+    unsigned char *scratch = reinterpret_cast<unsigned char *>(queue + kQCap) + (size_t)(threadIdx.x >> 5) * kScratch;
+    unsigned short *redo_list = reinterpret_cast<unsigned short *>(scratch);   // long rows: the literal pass's work list
+    uint4 *rows_s = reinterpret_cast<uint4 *>(scratch);                        // SHORT: the chunk's row table (no list there)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned c_begin = blockIdx.x * p.chunks_per_cta + min(blockIdx.x, p.chunks_rem);
@@ -518,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
     X.thr = x_thr; X.lev = x_lev; X.nlev = cb->n_levels;
     X.win = (cb->flags & ANTQ_CB_WELLSEP) ? cb->lim_idx : -1.0f;
     for (int i = threadIdx.x; i < X.nlev; i += kThreads) { x_thr[i] = cb->thr[i]; x_lev[i] = cb->level[i]; }
-    const PuK K = pu_load_k(cb);
+    const PuK K = pu_load_k(cb, p.lim, p.ovp);
     __syncthreads();
 
     int slot = 0;
@@ -604,8 +651,41 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
                     }
                 }
             }
+            // OliVe: vectors holding an outlier also go to the queue while it has room (a few per chunk at OliVe's design point
+            // of < 1 % outliers: settling them here would cost every chunk ~1 us of single-warp latency); when it is full --
+            // heavy-tailed data -- the rest of the chunk's pairs are settled here, densely (pu_redo_chunk).
+            if (p.ovp && !(p.debug & 4) && *reinterpret_cast<volatile unsigned *>(qcount) < (unsigned)kQCap) {
+                unsigned left = 0;
+                while (redo) {
+                    const int jj = __ffs(redo) - 1;
+                    redo &= redo - 1;
+                    const int v = jj * 32 + lane;
+                    const unsigned m = pu_vec_mask<T, UNIFORM>(sv[v], r, K, tab);
+                    unsigned pm = (m | (m >> 1)) & 0x55u;             // bit 2 p: pair p holds a wild element
+                    const unsigned slot_q = atomicAdd(qcount, (unsigned)__popc(pm));
+                    if (slot_q + (unsigned)__popc(pm) <= (unsigned)kQCap) {
+                        const T *xe = reinterpret_cast<const T *>(sv + v);
+                        unsigned k = slot_q;
+                        while (pm) {                                  // one entry per PAIR: the drain gives each a thread
+                            const int e = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            PuQEntry qe;
+                            qe.raw = make_uint4(__float_as_uint(A::to_f32(xe[e])), __float_as_uint(A::to_f32(xe[e + 1])), 0u, 0u);
+                            qe.v = (g.base / VEC + v) * VEC + e;      // ELEMENT index of the pair's even slot
+                            qe.s = r.s; qe.kx = -1.0f;                // kx < 0: the literal pair logic on the whole codebook
+                            queue[k++] = qe;
+                        }
+                    } else {
+                        for (unsigned k = slot_q; k < (unsigned)kQCap; k++) queue[k].kx = 0.0f;   // claimed, unused: no-ops
+                        left |= 1u << jj;
+                    }
+                }
+                redo = left;
+            }
         } else if (p.debug & 2) {
             for (int v = lane; v < nvec; v += 32) antq_stg_stream(ov + v, sv[v]);
+        } else if (p.ovp) {
+            for (int v = lane; v < nvec; v += 32) pu_redo_vec_ovp<T>(cb, X, sv[v], r.s, og + (long long)v * VEC);
         } else {
             redo = 0xffffffffu;                                       // bad scale: every vector, literally
         }
@@ -617,13 +697,13 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
                     redo &= redo - 1;
                     const int v = jj * 32 + lane;
                     PuRow rv = row_of(v);
-                    if (sizeof(T) == 2) rv.xl = pu_row_xl(p, rv.s);
+                    if (sizeof(T) == 2) rv.xl = pu_row_xl(K, rv.s);
                     pu_redo_vec<T, UNIFORM>(cb, X, sv[v], rv, K, tab, og + (long long)v * VEC);
                 }
             }
         } else {
             if (__any_sync(0xffffffffu, redo != 0) && !(p.debug & 4))
-                pu_redo_chunk<T, UNIFORM>(cb, X, sv, og, nvec, r, K, tab, redo, redo_list, lane);
+                pu_redo_chunk<T, UNIFORM>(cb, X, sv, og, nvec, r, K, tab, redo, redo_list, lane, p.ovp != 0);
         }
         if (g.tail > 0 && lane == 0) {                                 // ragged tail of a per-tensor view
             const T *xg = reinterpret_cast<const T *>(p.x) + g.base + (long long)nvec * VEC;
@@ -643,8 +723,16 @@ __global__ void __launch_bounds__(kThreads, 1) antq_pu_stream_kernel(const PuPar
         for (unsigned i = threadIdx.x; i < nq * VEC; i += kThreads) {
             const PuQEntry *qe = queue + i / VEC;
             const unsigned e = i % VEC;
-            const float xf = A::to_f32(reinterpret_cast<const T *>(&qe->raw)[e]);
-            oute[qe->v * VEC + e] = A::from_f32_rn(pu_elem_exact<UNIFORM>(xf, qe->s, qe->kx, K, tab));
+            const T *xe = reinterpret_cast<const T *>(&qe->raw);
+            if (qe->kx > 0.0f)
+                oute[qe->v * VEC + e] = A::from_f32_rn(pu_elem_exact<UNIFORM>(A::to_f32(xe[e]), qe->s, qe->kx, K, tab));
+        }
+        if (p.ovp) {                                                  // OliVe pairs holding an outlier: one thread per pair
+            for (unsigned i = threadIdx.x; i < nq; i += kThreads) {
+                const PuQEntry *qe = queue + i;
+                if (qe->kx < 0.0f)
+                    pu_exact_pair<T>(cb, X, __uint_as_float(qe->raw.x), __uint_as_float(qe->raw.y), qe->s, oute[qe->v], oute[qe->v + 1]);
+            }
         }
     }
 }
@@ -684,7 +772,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
     X.win = (p.cb->flags & ANTQ_CB_WELLSEP) ? p.cb->lim_idx : -1.0f;
     for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
     __syncthreads();
-    const PuK K = pu_load_k(p.cb);
+    const PuK K = pu_load_k(p.cb, p.lim, p.ovp);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -715,7 +803,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
                 if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
                 antq_stg_stream(xout + v, q);
                 if (wild) {
-                    if (sizeof(T) == 2) r.xl = pu_row_xl(p, r.s);
+                    if (sizeof(T) == 2) r.xl = pu_row_xl(K, r.s);
                     pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
                 }
             }
@@ -744,7 +832,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
     X.win = (p.cb->flags & ANTQ_CB_WELLSEP) ? p.cb->lim_idx : -1.0f;
     for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
     __syncthreads();
-    const PuK K = pu_load_k(p.cb);
+    const PuK K = pu_load_k(p.cb, p.lim, p.ovp);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -809,7 +897,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
                 if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
                 antq_stg_stream(xout + v, q);
                 if (wild) {
-                    if (sizeof(T) == 2) r.xl = pu_row_xl(p, r.s);
+                    if (sizeof(T) == 2) r.xl = pu_row_xl(K, r.s);
                     pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
                 }
             }
@@ -820,8 +908,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
 
 template <typename T, bool UNIFORM, bool XC, bool SHORT> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_pu_stream_kernel<T, UNIFORM, XC, SHORT>;
-    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kQCap * (int)sizeof(PuQEntry) + kNC * kListMax * 2 +
-                     (SHORT ? kNC * kRowsPerChunk * 16 : 0);
+    const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kQCap * (int)sizeof(PuQEntry) + kNC * kScratch;
     static unsigned long long configured = 0ull;                     // one bit per device ordinal
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -860,7 +947,7 @@ template <typename T, bool UNIFORM, bool XC> int launch_short(const PuParams &p,
 
 // Returns ANTQ_ENOTSUP for shapes the persistent kernel does not cover (more than 2^31 chunks).
 int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alpha_per_row, long long rows, long long cols,
-                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, cudaStream_t st) {
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, bool ovp, cudaStream_t st) {
     const int es = dtype == ANTQ_F32 ? 4 : 2;
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("ANTQ_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -891,6 +978,7 @@ int antq_launch_pu_stream(const void *x, void *out, const float *alpha, int alph
     p.alpha_per_row = alpha_per_row;
     p.gmax = info->gmax; p.lim = info->lim;
     p.debug = dbg;
+    p.ovp = ovp ? 1 : 0;
     const unsigned sms = (unsigned)antq_num_sms();
     const int ctas = (int)(p.total_chunks < sms ? p.total_chunks : sms);
     p.chunks_per_cta = p.total_chunks / (unsigned)ctas;

@@ -109,6 +109,9 @@ int antq_codebook_info_get(const void *codebook, antq_codebook_info *info_host, 
 #define ANTQ_CB_PU_XCBF  256  /* the same for bf16 inputs */
 #define ANTQ_CB_PU_E4M3  512  /* PU and every level / pu_c is exactly representable in FP8 e4m3 (all 4-bit int / flint / pot /
                                  float grids): the FP8 tensor-core path applies */
+#define ANTQ_CB_PU_OVP   1024 /* grid + outliers (OliVe): the NORMAL levels (|v| <= 32) are piecewise uniform (UNIFORM / XC bits describe
+                                 them); elements that stay below the first outlier threshold take the closed form, vectors holding
+                                 an outlier take the pair logic on the whole codebook */
 
 /* Fused scale -> nearest -> (OVP) -> STE -> rescale.  out may alias x (except OVP with odd numel).
  * `info` (host pointer, may be NULL) lets the call pick the row-table kernel

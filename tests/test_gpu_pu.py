@@ -150,6 +150,80 @@ def test_pu_short_rows_ragged_shapes(antq, kind, bit, signed, dtype):
         assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, 0)), ref, "short rows %d x %d" % (rows, cols))
 
 
+OLIVE = [("flint", True), ("flint", False), ("int", True), ("int", False)]
+
+
+@pytest.mark.parametrize("kind,signed", OLIVE)
+def test_pu_olive_pairs_exhaustive_fp16(antq, kind, signed):
+    """OliVe outlier-victim pairs through the closed-form kernel (normal levels by the closed form, vectors holding an
+    outlier by the pair logic): every fp16 bit pattern next to a small, a large and an outlier-sized neighbour, in both
+    slots of the pair, x 8 scales."""
+    from antq import _lib
+    grid, outl = orc.olive_grid(kind, 4, signed), orc.olive_outlier_grid(4, signed)
+    cb = _cb(antq, grid, outl)
+    assert cb.info.flags & _lib.CB_PU_OVP, (kind, signed)
+    allh = np.arange(65536, dtype=np.uint16).view(np.float16)
+    scales = SCALES[:8]
+    rows = []
+    for sc in scales:
+        a = np.float32(sc * grid.max())
+        for nb in (0.3, -0.8, 1.04, 1.3, 3.0, -7.0):                          # neighbour, in units of alpha
+            for slot in (0, 1):
+                r = np.empty(2 * 65536, dtype=np.float16)
+                r[slot::2] = allh
+                r[1 - slot::2] = np.float16(nb * a if signed or nb > 0 else -nb * a)
+                rows.append((r, a))
+    x = np.stack([r for r, _ in rows])
+    alpha = np.array([a for _, a in rows], dtype=np.float32)
+    xt = torch.from_numpy(x).to(dev())
+    assert antq.fakequant_plan(xt, cb, True, ovp=True, flags=_lib.FLAG_FORCE_PU) == 4
+    ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
+    y = antq.fakequant(xt, torch.from_numpy(alpha).to(dev()), cb, True, ovp=True, flags=_lib.FLAG_FORCE_PU)
+    assert_bit_equal(to_np(y), ref, "olive closed form %s %s" % (kind, signed))
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32", "bf16"])
+@pytest.mark.parametrize("kind,signed", OLIVE)
+def test_pu_olive_random(antq, kind, signed, dtype):
+    """Random data with a heavy tail (a few percent of outliers: the queue of outlier vectors overflows in some CTAs), NaN /
+    Inf, a dead row, a negative scale; per-row and per-tensor scales; the default plan of unsigned OliVe."""
+    from antq import _lib
+    rng = np.random.default_rng(3)
+    grid, outl = orc.olive_grid(kind, 4, signed), orc.olive_outlier_grid(4, signed)
+    cb = _cb(antq, grid, outl)
+    rows, cols = 64, 8192
+    x = (rng.standard_normal((rows, cols)) * 0.02).astype(np.float32)
+    x[rng.random((rows, cols)) < 0.002] *= 12                                # outliers
+    x[8:12][rng.random((4, cols)) < 0.2] *= 20                               # rows where a fifth of the elements are outliers
+    x[3, 5], x[3, 6], x[17, 100], x[30, 4095] = np.nan, 0.01, np.inf, -np.inf
+    x[20] = 0.0
+    if not signed:
+        x = np.abs(x)
+    alpha = (3.0 * np.nanstd(np.where(np.isfinite(x), x, np.nan), axis=1) * rng.uniform(0.7, 1.3, rows)).astype(np.float32)
+    alpha[20] = 0.0
+    alpha[40] = -0.05
+    tdt = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[dtype]
+    xt = torch.from_numpy(x).to(tdt)
+    xr = xt.float().numpy() if dtype == "bf16" else xt.numpy()
+    ref = orc.olive_forward(xr, alpha, grid, outl, per_row=True)
+    xd, ad = xt.to(dev()), torch.from_numpy(alpha).to(dev())
+    if not signed:
+        assert antq.fakequant_plan(xd, cb, True, ovp=True) == 4             # what an OPT fc2 input (post-ReLU) takes
+    else:
+        assert antq.fakequant_plan(xd, cb, True, ovp=True) == 1             # signed 4-bit keeps the two-phase chain
+    y = antq.fakequant(xd, ad, cb, True, ovp=True, flags=_lib.FLAG_FORCE_PU)
+    if dtype == "bf16":
+        reft = torch.from_numpy(ref).to(torch.bfloat16)
+        same = (y.cpu().view(torch.int16) == reft.view(torch.int16)) | (y.cpu().isnan() & reft.isnan())
+        assert bool(same.all()), int((~same).sum())
+    else:
+        assert_bit_equal(to_np(y), ref, "olive closed form per-row")
+        a0 = np.float32(0.07)
+        reft = orc.olive_forward(xr.reshape(-1), a0, grid, outl, per_row=False)
+        yt = antq.fakequant(xd.view(-1), torch.tensor([a0], device=dev()), cb, False, ovp=True, flags=_lib.FLAG_FORCE_PU)
+        assert_bit_equal(to_np(yt), reft, "olive closed form per-tensor")
+
+
 def test_default_plans(antq):
     """What a model actually hits: 8-bit int weights and post-ReLU 4-bit activations take the closed form, signed 4-bit
     keeps the chain, OliVe keeps its two-phase chain."""
