@@ -3,7 +3,7 @@ import csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 for n in ("r02_bench.json", "r02_bench_reference.json", "r02_sweep.jsonl", "r02_gemm_bench.json", "r02_launches.csv",
-          "r02_traffic_16384.csv", "r02_traffic_4096.csv", "r02_calibration.json", "r02_model_opt.json", "r02_model_resnet.json"):
+          "r02_traffic_16384.csv", "r02_traffic_4096.csv", "r02_calibration.json", "r02_model_opt.json", "r02_model_resnet.json", "r02_model_bert.json"):
     if os.path.exists(os.path.join(G, n)):
         shutil.copy(os.path.join(G, n), os.path.join(P, n))
 def parse(path):

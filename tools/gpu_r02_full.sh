@@ -7,6 +7,7 @@ python bench.py --steps 50 --warmup 5 > gpurun_out/r02_bench.json 2> gpurun_out/
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r02_bench_reference.json 2>/dev/null; cat gpurun_out/r02_bench_reference.json
 timeout 600 python tools/model_bench.py opt 2> gpurun_out/model_opt.err | grep '^{' | tail -1 > gpurun_out/r02_model_opt.json; cat gpurun_out/r02_model_opt.json; tail -2 gpurun_out/model_opt.err
 timeout 600 python tools/model_bench.py resnet 2> gpurun_out/model_resnet.err | grep '^{' | tail -1 > gpurun_out/r02_model_resnet.json; cat gpurun_out/r02_model_resnet.json; tail -2 gpurun_out/model_resnet.err
+timeout 600 python tools/model_bench.py bert 2> gpurun_out/model_bert.err | grep '^{' | tail -1 > gpurun_out/r02_model_bert.json; cat gpurun_out/r02_model_bert.json; tail -2 gpurun_out/model_bert.err
 python tools/calib_bench.py 2>/dev/null | tail -1 > gpurun_out/r02_calibration.json; cat gpurun_out/r02_calibration.json
 # DRAM traffic where it is observable: 16384^2 (1.07 GB per launch >> 126 MB L2), and the headline size for the read side
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:antq_stream -s 2 -c 2 --csv --log-file gpurun_out/r02_traffic_16384.csv python tools/quick_bench.py --rows 16384 --cols 16384 --nb 2 --reps 1 > /dev/null 2>&1

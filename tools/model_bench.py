@@ -4,12 +4,14 @@ O/llm/run_clm.py:603-613):
 
     python tools/model_bench.py opt      # one OPT-6.7B decoder layer (hidden 4096, ffn 16384, 32 heads), seq 2048, OliVe 4-bit
     python tools/model_bench.py resnet   # torchvision ResNet-50, batch 256 x 3 x 224 x 224 fp16, ANT flint-4 W + A
+    python tools/model_bench.py bert     # BERT-base-shaped encoder (12 x 768, ffn 3072), batch 32 x seq 128, ANT int/flint-4 W + A
 
 Each prints one JSON object: forward time of the plain fp16 model, of the quantized model (weights re-quantized every
 forward like the reference / eval-mode weight cache / fused tcgen05 Linear), the algorithmic bytes the fake-quant path
 touches per forward (sizeof(in) + sizeof(out) per quantized element) and the in-situ rate
-bytes / (t_quantized - t_plain) against the measured HBM peak.  Eager PyTorch, CUDA events, no CUDA graph: Python and
-launch overheads of the layer API are inside the numbers.
+bytes / (t_quantized - t_plain) against the measured HBM peak.  Eager PyTorch, CUDA events: Python and launch overheads of
+the layer API are inside the numbers; the `cuda_graph` entries replay the same forwards (plain and quantized, weight cache
+on) captured in a CUDA graph, which is how small-tensor models (BERT-base: 3 M-element activations) should be served.
 """
 import json
 import os
@@ -66,6 +68,39 @@ class OPTLayer(nn.Module):
         return x + self.fc2(F.relu(self.fc1(self.ln2(x))))
 
 
+class BertLayer(nn.Module):
+    """BERT-base encoder layer: the six nn.Linear the ANT BERT script quantizes (A/BERT/run_glue.py:538-546)."""
+
+    def __init__(self, h=768, ffn=3072, heads=12):
+        super().__init__()
+        self.heads = heads
+        self.q, self.k, self.v, self.o = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h)
+        self.ln1, self.ln2 = nn.LayerNorm(h), nn.LayerNorm(h)
+        self.fc1, self.fc2 = nn.Linear(h, ffn), nn.Linear(ffn, h)
+
+    def forward(self, x):
+        B, S, H = x.shape
+        sp = lambda t: t.view(B, S, self.heads, H // self.heads).transpose(1, 2)
+        a = F.scaled_dot_product_attention(sp(self.q(x)), sp(self.k(x)), sp(self.v(x)))
+        x = self.ln1(x + self.o(a.transpose(1, 2).reshape(B, S, H)))
+        return self.ln2(x + self.fc2(F.gelu(self.fc1(x))))
+
+
+def graphed(fn):
+    """fn() captured in a CUDA graph (after a warm-up on a side stream); returns the replay callable."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g.replay
+
+
 def quant_bytes(qmodel, per_forward_weights):
     """Algorithmic bytes of one forward: every activation quantizer call, plus the weights if they are re-quantized."""
     tot = [0]
@@ -77,10 +112,12 @@ def quant_bytes(qmodel, per_forward_weights):
     return tot, hs
 
 
-def run(model, x, args, fused_ok):
+def run(model, x, args, fused_ok, graph=True):
     res = {}
     with torch.no_grad():
         res["plain_ms"] = timeit(lambda: model(x))
+        if graph:
+            res["cuda_graph"] = {"plain_ms": round(timeit(graphed(lambda: model(x))), 3)}
         set_quantizer(args)  # noqa: F405
         q = quantize_model(model).to(dev).eval()  # noqa: F405
         enable_quantization(q)  # noqa: F405
@@ -103,6 +140,20 @@ def run(model, x, args, fused_ok):
                          "in_situ_GBps": round(tot[0] / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
                          "frac_of_hbm_peak": round(tot[0] / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None}
         L.CACHE_WEIGHTS, L.FUSED_LINEAR = True, False
+        if graph:
+            for m in q.modules():
+                if hasattr(m, "invalidate_weight_cache"):
+                    m.invalidate_weight_cache()
+            q(x)
+            tot, hs = quant_bytes(q, False)
+            q(x)
+            for h in hs:
+                h.remove()
+            ms = timeit(graphed(lambda: q(x)))
+            extra = ms - res["cuda_graph"]["plain_ms"]
+            res["cuda_graph"].update({"weight_cache_ms": round(ms, 3), "quant_bytes_per_forward": tot[0],
+                                      "in_situ_GBps": round(tot[0] / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
+                                      "frac_of_hbm_peak": round(tot[0] / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None})
     res["plain_ms"] = round(res["plain_ms"], 3)
     return res
 
@@ -118,6 +169,12 @@ if which == "opt":
     # the same layer with ANT-style grids (no outlier pairs) can take the fused tcgen05 Linear
     args2 = types.SimpleNamespace(**{**vars(args), "no_outlier": True})
     out["no_outlier_variant"] = run(model, x, args2, fused_ok=True)
+elif which == "bert":
+    model = nn.Sequential(*[BertLayer() for _ in range(12)]).to(dev).half().eval()
+    x = torch.randn(32, 128, 768, device=dev, dtype=torch.float16)
+    args = types.SimpleNamespace(mode="ant-int-flint", wbit=4, abit=4, w_up=150, a_up=150, w_low=75, a_low=75, percent=100, search=False)
+    out = {"workload": "BERT-base-shaped encoder (12 layers x 768, ffn 3072, 12 heads), batch 32 x seq 128, fp16, ANT int/flint-4 W + A"}
+    out.update(run(model, x, args, fused_ok=False))
 else:
     import torchvision
     model = torchvision.models.resnet50(weights=None).to(dev).half().eval()
