@@ -12,7 +12,7 @@ _PKG = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_PKG, "csrc", "libantq%s.so" % os.environ.get("ANTQ_LIB_SUFFIX", ""))   # suffix: tuning builds only
 
 F32, F16, BF16 = 0, 1, 2
-FLAG_OVP, FLAG_FORCE_FLAT, FLAG_FORCE_ROWS, FLAG_FORCE_PU, FLAG_NO_PU = 1, 2, 4, 8, 16
+FLAG_OVP, FLAG_FORCE_FLAT, FLAG_FORCE_ROWS, FLAG_FORCE_PU, FLAG_NO_PU, FLAG_FORCE_TILE = 1, 2, 4, 8, 16, 32
 CB_WELLSEP, CB_STE_EXACT, CB_SYMMETRIC, CB_OVP_OK, CB_SYMX, CB_PU, CB_PU_UNIFORM, CB_PU_XC16, CB_PU_XCBF, CB_PU_E4M3 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 CB_PU_OVP = 1024
 EINVAL, ENOTSUP, EALIGN = -1, -2, -3

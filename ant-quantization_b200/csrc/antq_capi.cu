@@ -105,6 +105,7 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
         chain = nt >= 1 && nt <= 31 && long_rows && (!ovp || ((info->flags & ANTQ_CB_OVP_OK) && cols % 2 == 0));
     }
     if (flags & ANTQ_FLAG_FORCE_ROWS) return chain ? 1 : ANTQ_ENOTSUP;
+    if (flags & ANTQ_FLAG_FORCE_TILE) return (pu && !ovp && cols % vec == 0 && (rows == 1 || cols / vec <= 127)) ? 5 : ANTQ_ENOTSUP;
     if (flags & ANTQ_FLAG_FORCE_PU) {
         if (pu && long_rows) return 4;
         if (pu && !ovp && rows > 1 && cols % vec == 0) return 5;
@@ -151,7 +152,7 @@ int antq_fakequant(const void *x, void *out, int16_t *codes, const float *alpha,
         default: break;
     }
     if (rc != ANTQ_ENOTSUP) return rc;
-    if (flags & (ANTQ_FLAG_FORCE_ROWS | ANTQ_FLAG_FORCE_PU)) return ANTQ_ENOTSUP;
+    if (flags & (ANTQ_FLAG_FORCE_ROWS | ANTQ_FLAG_FORCE_PU | ANTQ_FLAG_FORCE_TILE)) return ANTQ_ENOTSUP;
     // every shape, alignment and grid: the generic kernel (also the only one that emits int16 code indices)
     return antq_launch_flat(x, out, codes, alpha, alpha_per_row, rows, cols, dtype, cb, true, ovp, st);
 }

@@ -1009,7 +1009,8 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
     p.rows = rows; p.cols = cols;
     p.nvec = (unsigned)(n / vec);
     p.cols_vec = (unsigned)(cols / vec);
-    if (p.cols_vec > 127u) return ANTQ_ENOTSUP;                       // pu_row_local's 16-bit reciprocal
+    if (p.cols_vec > 127u && alpha_per_row && rows > 1) return ANTQ_ENOTSUP;   // pu_row_local's 16-bit reciprocal
+    if (!alpha_per_row || rows == 1) { alpha_per_row = 0; p.cols_vec = 1; }    // one scale: the row of a vector is never asked
     p.cols_magic = 65536u / p.cols_vec + 1u;
     p.cols_shift = -1;
     if ((p.cols_vec & (p.cols_vec - 1)) == 0) {

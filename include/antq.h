@@ -57,6 +57,7 @@ extern "C" {
 #define ANTQ_FLAG_FORCE_ROWS 4      /* testing: the row-table kernel (plan 1) or fail with ANTQ_ENOTSUP */
 #define ANTQ_FLAG_FORCE_PU   8      /* testing: the closed-form kernels (plans 4 / 5) or fail with ANTQ_ENOTSUP */
 #define ANTQ_FLAG_NO_PU     16      /* testing / A-B: never take the closed-form kernels */
+#define ANTQ_FLAG_FORCE_TILE 32     /* testing / A-B: the closed-form TILE kernel (plan 5) whatever the row length, or ANTQ_ENOTSUP */
 
 /* argument errors (negative); positive return values are cudaError_t */
 #define ANTQ_EINVAL  (-1)
