@@ -8,19 +8,29 @@
 //   t  = x * kx                      kx = fl32(fl32(1 / s) / c), c = the grid's unit: every level is fl32(k c), k integer
 //   mf = (t + M_e) - M_e             M_e = 1.5 * 2^23 * step_e rounds t to the octave's (power-of-two) step
 //   q  = fl32(clamp(mf, kmin, kmax) * c);   out = RN(fl32(q * s))      ((q - d) + d == q inside the window)
-// t is a few ulps off d / c, so an element whose t lies within delta_e = 2^(e - 19) of a midpoint -- or outside the
-// exact window, NaN, Inf, or in a row whose scale is not a positive finite number -- is redone with the literal
-// arithmetic (true division, the codebook's exact thresholds / the literal scan).  With 16-bit data that is ~1e-4 of
-// the elements, except in rows where a tie x / s == midpoint is representable.
+// t is a few ulps off d / c, so an element whose t lies within delta_e = 2^(e - 19) of a midpoint ("near") is settled by
+// comparing the two levels it lies between with the scan's own rounded distances on the true quotient (pu_elem_exact: no
+// search; equals the scan for every in-window element, tests/test_pu_model.py), and an element outside the exact window,
+// NaN, Inf, or in a row whose scale is not a positive finite number ("wild") takes the literal arithmetic (true division,
+// the codebook's exact thresholds / the literal scan).  With 16-bit data near elements are ~1e-4 of all, except in rows
+// where a tie x / s == midpoint is representable.  Where that work runs matters: a launch ends with its slowest warp,
+// so near vectors are parked in a CTA-wide queue and settled by all threads after the last chunk.
 //
-// Two execution shapes:
+// OliVe (ANTQ_CB_PU_OVP): the NORMAL levels are piecewise uniform and the window is cut below the first outlier
+// threshold, so the closed form covers every pair without an outlier; a pair holding an out-of-window element takes the
+// reference's pair logic (O/antquant/quant_modules.py:311-320) on the whole codebook.
+//
+// Execution shapes:
 //   antq_pu_stream_kernel   rows >= 512 elements / per-tensor: the persistent pipeline of antq_stream.cu (one CTA per
-//                           SM, 12 consumer warps, two private 4 KiB TMA stages each, chunk counter) -- minus the row
-//                           tables, the builder warps and the prologue: a row needs three scalars.
-//   antq_pu_short_kernel    shorter rows and scale groups (group-8/16/32, 1x1-conv weights): grid-stride over 16-byte
-//                           vectors, one IEEE division per VECTOR (for s) instead of one per element.
-// Bound: HBM in principle; ~17 fp32 / integer instructions per element keep the SM's issue slots ~85 % busy at the
-// HBM rate (measured: profiles/r02_notes.md).
+//                           SM, 16 consumer warps, two private 4 KiB TMA stages each, chunk counter) -- minus the row
+//                           tables, the builder warps and the prologue: a row needs three scalars.  SHORT mode: rows of
+//                           16-127 vectors on uniform grids, chunked flat, with a per-chunk table of row constants.
+//   antq_pu_short_kernel    shorter rows and scale groups (group-8/16/32, 1x1-conv weights): a warp owns a tile of 128
+//                           vectors, issues its loads first, computes the tile's row constants once (one row per lane,
+//                           shared through shared memory) and then runs the closed form.
+//   antq_pu_dynamic_kernel  the same with alpha = max|x| * ratio of each group computed in the kernel (one read of x).
+// Bound: HBM for uniform grids (12.75 instructions per element: the chain kernel's plateau); the per-octave-table grids
+// (15.7 instructions per element) are issue-bound at ~0.65 of the HBM rate (measured: profiles/r02_notes.md).
 #include <stdio.h>
 #include <stdlib.h>
 
