@@ -120,7 +120,7 @@ def test_pu_random(antq, kind, bit, signed, dtype):
     assert_bit_equal(to_np(xd), ref, "in place")
 
 
-@pytest.mark.parametrize("dtype", ["f16", "f32"])
+@pytest.mark.parametrize("dtype", ["f16", "f32", "bf16"])
 @pytest.mark.parametrize("kind,bit,signed", [("int", 8, True), ("flint", 4, False), ("flint", 5, True)])
 def test_pu_short_rows_ragged_shapes(antq, kind, bit, signed, dtype):
     """The tiled short-row kernel: row lengths that are not powers of two (rows straddle the 128-vector tiles, the row
@@ -129,7 +129,7 @@ def test_pu_short_rows_ragged_shapes(antq, kind, bit, signed, dtype):
     rng = np.random.default_rng(5 + bit)
     grid = orc.ant_grid(kind, bit, signed)
     cb = _cb(antq, grid)
-    vec = 8 if dtype == "f16" else 4
+    vec = 4 if dtype == "f32" else 8
     for cols_vec, rows in ((1, 1031), (3, 517), (5, 77), (9, 333), (25, 41), (63, 19), (127 if vec == 4 else 62, 23), (4, 2), (2, 1)):
         cols = cols_vec * vec
         x = (rng.standard_normal((rows, cols)) * 0.02).astype(np.float32)
@@ -141,13 +141,23 @@ def test_pu_short_rows_ragged_shapes(antq, kind, bit, signed, dtype):
             x = np.abs(x)
         if dtype == "f16":
             x = x.astype(np.float16)
+        if dtype == "bf16":
+            x = torch.from_numpy(x).to(torch.bfloat16).float().numpy()    # bf16-representable values, kept as fp32 for the oracle
         alpha = (np.abs(np.nan_to_num(x.astype(np.float32), nan=0)).max(1) * rng.uniform(0.5, 1.2, rows)).astype(np.float32)
         alpha[::5] = np.float32(0.05 * grid.max() / 8)                    # representable ties
         xt = torch.from_numpy(x).to(dev())
+        if dtype == "bf16":
+            xt = xt.to(torch.bfloat16)
         if rows > 1:
             assert antq.fakequant_plan(xt, cb, True) == 5, (cols_vec, rows)
         ref = orc.ant_forward(x, alpha, grid, per_row=True)
-        assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, 0)), ref, "short rows %d x %d" % (rows, cols))
+        if dtype == "bf16":
+            y = antq.fakequant(xt, torch.from_numpy(alpha).to(dev()), cb, True).cpu()
+            reft = torch.from_numpy(ref).to(torch.bfloat16)
+            same = (y.view(torch.int16) == reft.view(torch.int16)) | (y.isnan() & reft.isnan())
+            assert bool(same.all()), ("short rows bf16 %d x %d" % (rows, cols), int((~same).sum()))
+        else:
+            assert_bit_equal(to_np(_run(antq, x, alpha, cb, True, 0)), ref, "short rows %d x %d" % (rows, cols))
 
 
 OLIVE = [("flint", True), ("flint", False), ("int", True), ("int", False)]
