@@ -42,7 +42,7 @@ def time_graph(step, reps):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 
-def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20, alpha_scale=1.0):
+def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20, alpha_scale=1.0, data="randn*0.02"):
     dev = torch.device("cuda:0")
     dt = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[dtype]
     es = 4 if dtype == "f32" else 2
@@ -55,9 +55,15 @@ def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20, alpha_scale
     g = torch.Generator(device="cuda").manual_seed(n + bit)
     xs, als, outs = [], [], []
     for _ in range(nb):
-        x = torch.randn(n, n, device=dev, generator=g) * 0.02
-        if not signed:
-            x = x.abs()
+        x = torch.randn(n, n, device=dev, generator=g)
+        if data.startswith("tail"):                                   # 0.1 % of the entries x 20 / x 60
+            x = torch.where(torch.rand(n, n, device=dev, generator=g) < 1e-3, x * float(data[4:]), x)
+        elif data == "relu":                                          # post-ReLU, half the entries zero
+            x = torch.relu(x)
+        else:
+            x = x * 0.02
+            if not signed:
+                x = x.abs()
         x = x.to(dt)
         if gran == "tensor":
             v, per_row = x, False
@@ -86,8 +92,41 @@ def case(n, kind, bit, signed, olive, gran, dtype, flags=0, reps=20, alpha_scale
     pk, src = peak()
     gbs = n * n * es * 2 / us / 1e3
     return {"n": n, "type": ("olive-" if olive else "") + kind, "bit": bit, "signed": signed, "granularity": gran,
-            "dtype": dtype, "plan": plan, "us": round(us, 2), "GBps": round(gbs, 1), "frac": round(gbs / pk, 3),
+            "dtype": dtype, "data": data, "plan": plan, "us": round(us, 2), "GBps": round(gbs, 1), "frac": round(gbs / pk, 3),
             "peak": pk, "peak_source": src, "nb": nb}
+
+
+def codes_case(n, kind, olive):
+    dev = torch.device("cuda:0")
+    nb = 6
+    if olive:
+        cb = antq.prepare_codebook(codebooks.olive_grid(kind, 4, True).to(dev), codebooks.olive_outliers(4, True).to(dev))
+    else:
+        cb = antq.prepare_codebook(codebooks.ant_grid(kind, 4, True).to(dev))
+    g = torch.Generator(device="cuda").manual_seed(n)
+    xs = [(torch.randn(n, n, device=dev, generator=g) * 0.02).to(torch.float16) for _ in range(nb)]
+    als = [(x.float().abs().amax(1) * 0.9).contiguous() for x in xs]
+    if olive:
+        als = [torch.full_like(a, float(3 * x.float().std())) for a, x in zip(als, xs)]
+    codes = [antq.encode_p4(x, a, cb, True, ovp=olive)[0] for x, a in zip(xs, als)]
+    outs = [torch.empty_like(x) for x in xs]
+
+    def enc():
+        for i in range(nb):
+            antq.encode_p4(xs[i], als[i], cb, True, ovp=olive, count_inexact=False)
+
+    def dec():
+        for i in range(nb):
+            antq.decode_p4(codes[i], als[i], cb, xs[i].shape, torch.float16, True, ovp=olive, out=outs[i])
+    pk, src = peak()
+    r = {"n": n, "type": ("olive-" if olive else "") + kind, "bit": 4, "signed": True, "granularity": "row", "dtype": "f16",
+         "plan": "packed 4-bit codes (P4)", "peak": pk, "peak_source": src}
+    for name, fn in (("encode", enc), ("decode", dec)):
+        us = time_graph(fn, 10) / nb
+        gbs = n * n * 2.5 / us / 1e3
+        r[name] = {"us": round(us, 2), "GBps": round(gbs, 1), "frac": round(gbs / pk, 3)}
+    r["note"] = "2.5 algorithmic bytes per element (fp16 one way, 4-bit codes the other)"
+    return r
 
 
 def main():
@@ -132,6 +171,19 @@ def main():
             for t in (("flint", 4, True, False), ("int", 8, True, False), ("flint", 4, False, False)):
                 for gr in ("row", "g32"):
                     emit(case(4096, *t, gr, dt))
+        # the other synthetic inputs of SURVEY 8(d): heavy tails (clipped values, OliVe outliers), post-ReLU data
+        for t, d in ((("flint", 4, True, False), "tail20"), (("flint", 4, True, False), "tail60"), (("int", 8, True, False), "tail20"),
+                     (("flint", 4, True, True), "tail20"), (("flint", 4, True, True), "tail60"),
+                     (("flint", 4, False, False), "relu"), (("int", 8, False, False), "relu"), (("flint", 4, False, True), "relu")):
+            for gr in ("row", "tensor"):
+                emit(case(4096, *t, gr, "f16", data=d))
+        # int of every width
+        for b in (3, 5, 7):
+            for gr in ("row", "g32"):
+                emit(case(4096, "int", b, True, False, gr, "f16"))
+        # packed 4-bit codes: encode (2 B in + 0.5 B out per element) and decode (0.5 B in + 2 B out)
+        emit(codes_case(4096, "flint", False))
+        emit(codes_case(4096, "flint", True))
         # OliVe unsigned (post-ReLU activations, e.g. OPT's fc2 input): alpha = 3 std(x) of half-normal data leaves 4 % of the
         # elements beyond the first outlier threshold (the rows above); with alpha = 3 sigma of the underlying normal it is
         # 0.07 %, OliVe's design point -- and the other kernel (the two-phase chain) on the same data
