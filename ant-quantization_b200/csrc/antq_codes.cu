@@ -14,6 +14,8 @@
 //                                            NOT reproduced by decoding the code (out-of-window STE rounding, NaN, Inf)
 //   antq_decode_p4   codes, alpha -> values  RN(fl32(level * s)): bit-identical to antq_fakequant wherever the
 //                                            count above is zero
+#include <type_traits>
+
 #include "antq_common.cuh"
 
 namespace {
@@ -29,6 +31,7 @@ struct CodesParams {
     long long n, cols;         // elements; elements per row
     int alpha_per_row, ovp;
     unsigned int *n_inexact;
+    int cols_shift;            // log2(cols) when cols is a power of two, else -1 (decode: the row of a thread without a 64-bit division)
 };
 
 // one thread = 8 consecutive elements = 4 code bytes
@@ -128,14 +131,20 @@ template <typename T, bool OVP> __global__ void __launch_bounds__(kThreads) antq
     } else {
         for (int b = 0; b < cnt / 2; b++) w[b >> 2] |= (unsigned)src[b] << (8 * (b & 3));
     }
-    long long row = p.alpha_per_row ? i0 / p.cols : 0;
-    long long col = p.alpha_per_row ? i0 - row * p.cols : 0;
+    long long row = 0, col = 0;
+    if (p.alpha_per_row) {
+        if (p.cols_shift >= 0) row = i0 >> p.cols_shift;
+        else if (p.n <= 0xffffffffLL) row = (long long)((unsigned)i0 / (unsigned)p.cols);
+        else row = i0 / p.cols;
+        col = i0 - row * p.cols;
+    }
     float s = __fdiv_rn(p.alpha[row], gmax);
+    const bool one_row = !p.alpha_per_row || col + 16 <= p.cols;      // the usual case: all 16 elements share the scale
     T ov[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
         if (e + 1 < cnt) {
-            if (p.alpha_per_row && col == p.cols) { col = 0; row++; s = __fdiv_rn(p.alpha[row], gmax); }
+            if (!one_row && col == p.cols) { col = 0; row++; s = __fdiv_rn(p.alpha[row], gmax); }
             col += 2;                                                  // rows are even: a pair never straddles one
             const unsigned byte = (w[e >> 3] >> (4 * (e & 7))) & 0xffu;
             const int ne = byte & 15, no = byte >> 4;
@@ -154,6 +163,57 @@ template <typename T, bool OVP> __global__ void __launch_bounds__(kThreads) antq
         for (int k = 0; k < (int)(16 * sizeof(T) / 16); k++) antq_stg_stream(reinterpret_cast<uint4 *>(dst) + k, srcv[k]);
     } else {
         for (int e = 0; e < cnt; e++) dst[e] = ov[e];
+    }
+}
+
+// The fast decoder (cols a multiple of the 16-byte vector, 16-byte aligned output, 4-byte aligned codes): a warp owns kDecU
+// x 32 consecutive vectors; every load (VEC / 2 code bytes per lane) and every 16-byte store is fully coalesced, and kDecU
+// of each are in flight per lane.  The one-thread-16-elements kernel above wrote 16 bytes per lane at a 32-byte stride:
+// 18.8 us per 4096^2 fp16 against ~8 here (profiles/r02_notes.md).
+constexpr int kDecU = 4;
+template <typename T, bool OVP> __global__ void __launch_bounds__(kThreads) antq_decode_p4_fast_kernel(const CodesParams p) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;                                      // elements per 16-byte store: 8 or 4
+    typedef typename std::conditional<VEC == 8, unsigned, unsigned short>::type code_t;    // VEC / 2 code bytes
+    __shared__ float s_grid[32];
+    const AntqCodebook *__restrict__ cb = p.cb;
+    const int kn = cb->n_normal;
+    if (threadIdx.x < 32) s_grid[threadIdx.x] = threadIdx.x < cb->n_entries ? cb->grid[threadIdx.x] : 0.0f;
+    __syncthreads();
+    const float gmax = cb->gmax;
+    const long long nvec = p.n / VEC;
+    const unsigned cols_vec = (unsigned)(p.cols / VEC);
+    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long v0 = warp_g * (kDecU * 32) + lane;
+    const code_t *cv = reinterpret_cast<const code_t *>(p.codes);
+    uint4 *ov = reinterpret_cast<uint4 *>(p.out);
+    unsigned w[kDecU];
+#pragma unroll
+    for (int j = 0; j < kDecU; j++) {
+        const long long v = v0 + j * 32;
+        w[j] = v < nvec ? (unsigned)__ldg(cv + v) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kDecU; j++) {
+        const long long v = v0 + j * 32;
+        if (v >= nvec) break;
+        long long row = 0;
+        if (p.alpha_per_row) row = p.cols_shift >= 0 ? (v * VEC) >> p.cols_shift : (nvec <= 0xffffffffLL ? (long long)((unsigned)v / cols_vec) : v / cols_vec);
+        const float s = __fdiv_rn(__ldg(p.alpha + row), gmax);
+        T o[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; e += 2) {
+            const unsigned byte = (w[j] >> (4 * e)) & 0xffu;
+            const int ne = byte & 15, no = byte >> 4;
+            float ve, vo;
+            if (OVP && no == 15) { ve = s_grid[kn + ne]; vo = 0.0f; }
+            else if (OVP && ne == 15) { vo = s_grid[kn + no]; ve = 0.0f; }
+            else { ve = s_grid[ne]; vo = s_grid[no]; }
+            o[e] = A::from_f32_rn(__fmul_rn(ve, s));
+            o[e + 1] = A::from_f32_rn(__fmul_rn(vo, s));
+        }
+        antq_stg_stream(ov + v, *reinterpret_cast<const uint4 *>(o));
     }
 }
 
@@ -234,6 +294,27 @@ int antq_decode_p4(const uint8_t *codes, void *out, const float *alpha, int alph
     CodesParams p = {};
     p.codes = const_cast<unsigned char *>(codes); p.out = out; p.alpha = alpha; p.cb = (const AntqCodebook *)codebook;
     p.n = n; p.cols = cols; p.alpha_per_row = alpha_per_row && rows > 1; p.ovp = ovp;
+    p.cols_shift = -1;
+    if (cols > 0 && (cols & (cols - 1)) == 0) { int sh = 0; while ((1LL << sh) < cols) sh++; p.cols_shift = sh; }
+    const int vec = 16 / esize(dtype);
+    if (cols % vec == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)codes % 4 == 0) {
+        const long long warps = (n / vec + kDecU * 32 - 1) / (kDecU * 32);
+        const long long fctas = (warps * 32 + kThreads - 1) / kThreads;
+        if (fctas <= 0x7fffffffLL) {
+#define ANTQ_DECF(T)                                                                              \
+    do {                                                                                          \
+        if (ovp) antq_decode_p4_fast_kernel<T, true><<<(unsigned)fctas, kThreads, 0, st>>>(p);    \
+        else antq_decode_p4_fast_kernel<T, false><<<(unsigned)fctas, kThreads, 0, st>>>(p);       \
+    } while (0)
+            switch (dtype) {
+                case ANTQ_F32: ANTQ_DECF(float); break;
+                case ANTQ_F16: ANTQ_DECF(__half); break;
+                case ANTQ_BF16: ANTQ_DECF(__nv_bfloat16); break;
+            }
+#undef ANTQ_DECF
+            return (int)cudaGetLastError();
+        }
+    }
     const long long ctas = (n / 16 + kThreads) / kThreads;
     if (ctas > 0x7fffffffLL) return ANTQ_ENOTSUP;
 #define ANTQ_DEC(T)                                                                          \
