@@ -18,6 +18,9 @@
 
 #include "antq_common.cuh"
 
+int antq_launch_pu_encode(const void *x, unsigned char *codes, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, unsigned int *n_inexact, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -258,6 +261,11 @@ int antq_encode_p4(const void *x, uint8_t *codes, const float *alpha, int alpha_
     if (n_inexact) {
         cudaError_t e = cudaMemsetAsync(n_inexact, 0, sizeof(unsigned int), st);
         if (e != cudaSuccess) return (int)e;
+    }
+    if (!ovp && !(flags & ANTQ_FLAG_NO_PU)) {                         // closed form where the grid allows it (antq_pu.cu)
+        const int rc = antq_launch_pu_encode(x, codes, alpha, alpha_per_row, rows, cols, dtype, (const AntqCodebook *)codebook, info,
+                                             n_inexact, st);
+        if (rc != ANTQ_ENOTSUP) return rc;
     }
     CodesParams p = {};
     p.x = x; p.codes = codes; p.alpha = alpha; p.cb = (const AntqCodebook *)codebook;

@@ -291,8 +291,11 @@ __device__ __forceinline__ uint4 pu_vec(const uint4 raw, const PuRow &r, const P
 // (ascending grids: the later entry).  Valid for every element inside the window, near a midpoint or not; elements
 // outside it get garbage here and are rewritten by the literal path.  Proof sketch: |t - d / c| is a few ulps, far
 // below step / 2, so rank(d) is the index of one of the two candidates (ANTQ_CB_WELLSEP: adjacent thresholds decide).
+// The two-candidate decision for one in-window element: the winning level as k (units of c), its value q = fl32(k c) and
+// the true quotient d.
 template <bool UNIFORM>
-__device__ __forceinline__ float pu_elem_exact(const float xf, const float s, const float kx, const PuK &K, const float2 *tab) {
+__device__ __forceinline__ float pu_elem_exact_k(const float xf, const float s, const float kx, const PuK &K, const float2 *tab,
+                                                 float &q, float &d) {
     const float t = __fmul_rn(xf, kx);
     float M = 12582912.0f, step = 1.0f;
     if (!UNIFORM) {
@@ -303,10 +306,19 @@ __device__ __forceinline__ float pu_elem_exact(const float xf, const float s, co
     const float rr = __fsub_rn(t, mf);
     const float oth = __fadd_rn(mf, copysignf(step, rr));
     const float k1 = fminf(fmaxf(mf, K.kmin), K.kmax), k2 = fminf(fmaxf(oth, K.kmin), K.kmax);
-    const float ql = __fmul_rn(fminf(k1, k2), K.c), qh = __fmul_rn(fmaxf(k1, k2), K.c);
-    const float d = __fdiv_rn(xf, s);
+    const float kl = fminf(k1, k2), kh = fmaxf(k1, k2);
+    const float ql = __fmul_rn(kl, K.c), qh = __fmul_rn(kh, K.c);
+    d = __fdiv_rn(xf, s);
     const float dl = fabsf(__fsub_rn(d, ql)), dh = fabsf(__fsub_rn(d, qh));
-    return antq_ste_rescale(dh <= dl ? qh : ql, d, s);
+    const bool up = dh <= dl;
+    q = up ? qh : ql;
+    return up ? kh : kl;
+}
+template <bool UNIFORM>
+__device__ __forceinline__ float pu_elem_exact(const float xf, const float s, const float kx, const PuK &K, const float2 *tab) {
+    float q, d;
+    (void)pu_elem_exact_k<UNIFORM>(xf, s, kx, K, tab, q, d);
+    return antq_ste_rescale(q, d, s);
 }
 template <typename T, bool UNIFORM>
 __device__ __noinline__ uint4 pu_vec_exact(const uint4 raw, const float s, const float kx, const PuK K, const float2 *tab) {
@@ -916,6 +928,103 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
     }
 }
 
+// ==================================================================================================
+// Packed 4-bit codes by the closed form (antq_encode_p4's fast path: piecewise-uniform grids of <= 16 entries whose levels
+// are exact in e4m3, no pairs).  Tile structure of antq_pu_short_kernel; the level k of an element becomes its code
+// through a 256-entry table indexed by k's e4m3 byte (4-bit grids have at most 4 significant bits).  Near-midpoint
+// elements: the two-candidate decision; wild elements (outside the exact window, NaN, Inf, bad scale): the literal scan,
+// which is also where decoding may fail to reproduce the fake-quant value (n_inexact).
+// ==================================================================================================
+__device__ __forceinline__ unsigned pu_e4m3x2(float lo, float hi) {                      // two floats -> two e4m3 bytes
+    unsigned short r;
+    asm("{ cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2; }" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <typename T, bool UNIFORM>
+__global__ void __launch_bounds__(kShortThreads, 3) antq_pu_encode_kernel(const PuParams p, unsigned char *__restrict__ codes,
+                                                                           unsigned int *__restrict__ n_inexact) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    __shared__ float2 tab[UNIFORM ? 1 : 512];
+    __shared__ unsigned char lut[256];
+    const AntqCodebook *__restrict__ cb = p.cb;
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = cb->pu_tab[i & 255];
+    }
+    for (int i = threadIdx.x; i < 256; i += kShortThreads) lut[i] = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < cb->n_levels) {
+        const float k = __fdiv_rn(cb->level[threadIdx.x], cb->pu_c);
+        lut[pu_e4m3x2(k, 0.0f) & 0xffu] = (unsigned char)cb->level_code[threadIdx.x];
+    }
+    __syncthreads();
+    const PuK K = pu_load_k(cb, p.lim, 0);
+    const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned ntiles = (p.nvec + kTileVec - 1) / kTileVec;
+    const unsigned nwarps = gridDim.x * kShortWarps;
+    unsigned bad = 0;
+    for (unsigned t = blockIdx.x * kShortWarps + warp; t < ntiles; t += nwarps) {
+        const unsigned v0 = t * kTileVec;
+        const unsigned vend = min(v0 + kTileVec, p.nvec);
+        uint4 raw[kVPL];
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            raw[j] = make_uint4(0, 0, 0, 0);
+            if (v < vend) raw[j] = antq_ldg_stream(xin + v);
+        }
+        unsigned prev_row = 0xffffffffu;
+        PuRow r;
+        r.s = 1.0f; r.kx = 1.0f; r.xl = 0.0f; r.xl2 = r.xlo2 = r.xhi2 = 0; r.ok = false;
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            if (v >= vend) break;
+            const unsigned row = p.alpha_per_row ? pu_row_of(p, v) : 0u;
+            if (row != prev_row) { r = pu_row<T>(__ldg(p.alpha + row), p, K, true); prev_row = row; }
+            float f[VEC], kk[VEC];
+            PuIO<T>::unpack(raw[j], f);
+            unsigned wild = r.ok ? 0u : (1u << VEC) - 1u;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                bool near = false;
+                const float t_ = __fmul_rn(f[e], r.kx);
+                float M = 12582912.0f, hd = __fmaf_rn(fabsf(t_), -1.9073486328125e-06f, 0.5f);
+                if (!UNIFORM) { const float2 md = tab[__float_as_uint(t_) >> 23]; M = md.x; hd = md.y; }
+                const float mf = __fsub_rn(__fadd_rn(t_, M), M);
+                near = fabsf(__fsub_rn(t_, mf)) >= hd;
+                kk[e] = fminf(fmaxf(mf, K.kmin), K.kmax);
+                if (!(fabsf(f[e]) <= r.xl)) wild |= 1u << e;          // outside the exact window, NaN, Inf
+                else if (near) { float q, d; kk[e] = pu_elem_exact_k<UNIFORM>(f[e], r.s, r.kx, K, tab, q, d); }
+            }
+            unsigned packed = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; e += 2) {
+                const unsigned b2 = pu_e4m3x2(kk[e], kk[e + 1]);
+                packed |= ((unsigned)lut[b2 & 0xffu] | ((unsigned)lut[b2 >> 8] << 4)) << (4 * e);
+            }
+            while (wild) {                                            // literally: the scan, and the check the codes can be trusted
+                const int e = __ffs(wild) - 1;
+                wild &= wild - 1;
+                float xf = f[0];
+#pragma unroll
+                for (int i = 1; i < VEC; i++) xf = e == i ? f[i] : xf;
+                const float d = __fdiv_rn(xf, r.s);
+                int code;
+                const float q = antq_scan_literal(cb->grid, cb->n_entries, d, code);
+                const T ref = A::from_f32_rn(antq_ste_rescale(q, d, r.s));
+                const T dec = A::from_f32_rn(__fmul_rn(code >= 0 ? q : 0.0f, r.s));
+                if (A::bits(ref) != A::bits(dec) || code < 0 || code > 15) bad++;
+                packed = (packed & ~(0xfu << (4 * e))) | ((unsigned)(code & 15) << (4 * e));
+            }
+            if (VEC == 8) reinterpret_cast<unsigned *>(codes)[v] = packed;
+            else reinterpret_cast<unsigned short *>(codes)[v] = (unsigned short)packed;
+        }
+    }
+    if (bad && n_inexact) atomicAdd(n_inexact, bad);
+}
+
 template <typename T, bool UNIFORM, bool XC, bool SHORT> int launch_stream(const PuParams &p, int ctas, cudaStream_t st) {
     auto kernel = antq_pu_stream_kernel<T, UNIFORM, XC, SHORT>;
     const int smem = kNS * kChunkMax + 512 * 8 + 2 * ANTQ_MAX_GRID * 4 + kNS * 8 + 16 + kQCap * (int)sizeof(PuQEntry) + kNC * kScratch;
@@ -1104,6 +1213,48 @@ int antq_launch_pu_dynamic(const void *x, void *out, float *alpha_out, float rat
         case ANTQ_F32: ANTQ_PU_GO(float, false); break;
         case ANTQ_F16: if (xc) ANTQ_PU_GO(__half, true); else ANTQ_PU_GO(__half, false); break;
         case ANTQ_BF16: if (xc) ANTQ_PU_GO(__nv_bfloat16, true); else ANTQ_PU_GO(__nv_bfloat16, false); break;
+        default: return ANTQ_EINVAL;
+    }
+#undef ANTQ_PU_GO
+    return (int)cudaGetLastError();
+}
+
+// antq_encode_p4's fast path.  ENOTSUP: the caller falls back to the literal encoder (antq_codes.cu).
+int antq_launch_pu_encode(const void *x, unsigned char *codes, const float *alpha, int alpha_per_row, long long rows, long long cols,
+                          int dtype, const AntqCodebook *cb, const antq_codebook_info *info, unsigned int *n_inexact, cudaStream_t st) {
+    const int es = dtype == ANTQ_F32 ? 4 : 2;
+    const int vec = 16 / es;
+    const long long n = rows * cols;
+    const int need = ANTQ_CB_PU | ANTQ_CB_PU_E4M3 | ANTQ_CB_WELLSEP | ANTQ_CB_STE_EXACT;
+    if (!info || (info->flags & need) != need || info->n_entries > 16) return ANTQ_ENOTSUP;
+    if (n == 0 || cols % vec || (n / vec) > 0x7fffffffLL || (uintptr_t)x % 16 || (uintptr_t)codes % 4) return ANTQ_ENOTSUP;
+    PuParams p = {};
+    p.x = x; p.alpha = alpha; p.cb = cb;
+    p.rows = rows; p.cols = cols;
+    p.nvec = (unsigned)(n / vec);
+    p.cols_vec = (unsigned)(cols / vec);
+    p.cols_shift = -1;
+    if ((p.cols_vec & (p.cols_vec - 1)) == 0) {
+        int sh = 0;
+        while ((1u << sh) < p.cols_vec) sh++;
+        p.cols_shift = sh;
+    }
+    p.alpha_per_row = (alpha_per_row && rows > 1) ? 1 : 0;
+    p.gmax = info->gmax; p.lim = info->lim;
+    const long long tiles = ((long long)p.nvec + kTileVec - 1) / kTileVec;
+    const long long want = (tiles + kShortWarps - 1) / kShortWarps;
+    const long long cap = (long long)antq_num_sms() * 3;
+    const int ctas = (int)(want < cap ? want : cap);
+    const bool uni = (info->flags & ANTQ_CB_PU_UNIFORM) != 0;
+#define ANTQ_PU_GO(T)                                                                                       \
+    do {                                                                                                    \
+        if (uni) antq_pu_encode_kernel<T, true><<<ctas, kShortThreads, 0, st>>>(p, codes, n_inexact);       \
+        else antq_pu_encode_kernel<T, false><<<ctas, kShortThreads, 0, st>>>(p, codes, n_inexact);          \
+    } while (0)
+    switch (dtype) {
+        case ANTQ_F32: ANTQ_PU_GO(float); break;
+        case ANTQ_F16: ANTQ_PU_GO(__half); break;
+        case ANTQ_BF16: ANTQ_PU_GO(__nv_bfloat16); break;
         default: return ANTQ_EINVAL;
     }
 #undef ANTQ_PU_GO
