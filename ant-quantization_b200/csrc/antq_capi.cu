@@ -117,7 +117,10 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     // 5 to 8 bit.  Measured side by side in profiles/r02_notes.md.
     // (OliVe's signed 4-bit codebooks keep the two-phase chain: 7 thresholds in phase one, 13.2-15.1 us)
     const bool ovp2_fast = ovp && info && (info->flags & ANTQ_CB_SYMMETRIC) && nt <= 15;
-    if (chain && (nt <= 7 || !pu || ovp2_fast)) return 1;
+    // fp32 I/O: the chain works on one element per register there (no packed pairs) and loses to the closed form even at 7
+    // thresholds (31.3 vs 25.5 us per 4096^2, flint-4 signed)
+    const bool f32_pu = dtype == ANTQ_F32 && pu && !ovp && long_rows;
+    if (chain && (nt <= 7 || !pu || ovp2_fast) && !f32_pu) return 1;
     if (pu && long_rows) return 4;
     if (chain) return 1;
     const bool short_rows = info && !codes && aligned && rows > 1 && cols < kRowsMinCols && cols % vec == 0;

@@ -46,6 +46,9 @@ def test_abi_basics_without_gpu():
                               n_mag=128, mid=128, ovp_index=-1)
     plan = lambda info, r, c, fl=0, codes=None: _lib.lib.antq_fakequant_plan(ctypes.byref(info), r, c, _lib.F16, fl, 256, 512, codes)
     assert plan(pu7, 4096, 4096) == 1 and plan(pu7, 4096, 64) == 5 and plan(pu7, 4096, 64, _lib.FLAG_NO_PU) == 3
+    # fp32 I/O: the closed form even for a 7-threshold grid (the chain has no packed pairs there)
+    assert _lib.lib.antq_fakequant_plan(ctypes.byref(pu7), 4096, 4096, _lib.F32, 0, 256, 512, None) == 4
+    assert _lib.lib.antq_fakequant_plan(ctypes.byref(pu7), 4096, 4096, _lib.F32, _lib.FLAG_NO_PU, 256, 512, None) == 1
     assert plan(pu127, 4096, 4096) == 4 and plan(pu127, 1, 12345) == 4 and plan(pu127, 4096, 32) == 5
     assert plan(pu127, 4096, 4096, _lib.FLAG_NO_PU) == 2 and plan(pu127, 4096, 4096, 0, 1024) == 2
     assert plan(pu7, 4096, 4096, _lib.FLAG_FORCE_PU) == 4 and plan(pu7, 4096, 4096, _lib.FLAG_OVP | _lib.FLAG_FORCE_PU) == _lib.ENOTSUP
