@@ -122,7 +122,10 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     const bool f32_pu = dtype == ANTQ_F32 && pu && !ovp && long_rows;
     // bf16 I/O, uniform grids (int-k): 14.7 / 13.7 us (per-row / per-tensor) against the chain's 18.2 / 15.8
     const bool bf16_pu = dtype == ANTQ_BF16 && pu && !ovp && long_rows && (info->flags & ANTQ_CB_PU_UNIFORM);
-    if (chain && (nt <= 7 || !pu || ovp2_fast) && !f32_pu && !bf16_pu) return 1;
+    // fp16 I/O, uniform grids, per-row scales: 13.7 us against the chain's 14.7 (its SYMX path: one extra compare per pair);
+    // with one scale the chain keeps a small edge (13.3 vs 13.6)
+    const bool f16_int_pu = dtype == ANTQ_F16 && pu && !ovp && long_rows && rows > 1 && (info->flags & ANTQ_CB_PU_UNIFORM);
+    if (chain && (nt <= 7 || !pu || ovp2_fast) && !f32_pu && !bf16_pu && !f16_int_pu) return 1;
     if (pu && long_rows) return 4;
     if (chain) return 1;
     const bool short_rows = info && !codes && aligned && rows > 1 && cols < kRowsMinCols && cols % vec == 0;

@@ -367,10 +367,8 @@ def test_stream_kernel_signed_int(antq, bit, dtype):
     if dtype == "f16":
         x = x.astype(np.float16)
     ref = orc.ant_forward(x, alpha, grid, per_row=True)
-    # up to 7 thresholds after folding signs the chain is the default; beyond, the closed form (plan 4) is, and
     # FORCE_ROWS still runs the chain
-    # (fp32 I/O: the closed form at every width)
-    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True) == (1 if bit <= 4 and dtype != "f32" else 4)
+    assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True) == 4       # int-k, per-row scales: the closed form
     assert antq.fakequant_plan(torch.from_numpy(x).to(dev()), cb, True, flags=_lib.FLAG_FORCE_ROWS) == 1
     y = _run_ant(antq, x, alpha, grid, True, _lib.FLAG_FORCE_ROWS)
     assert_bit_equal(y, ref, "signed int-%d %s" % (bit, dtype))
@@ -535,7 +533,7 @@ def test_full_size_properties(antq, kind, olive):
         grid, outl = orc.ant_grid(kind, 4, True), None
         cb = _cb(antq, grid)
         alpha = (x.float().abs().amax(1) * 0.85).contiguous()
-    assert antq.fakequant_plan(x, cb, True, ovp=olive) == 1
+    assert antq.fakequant_plan(x, cb, True, ovp=olive) == (4 if kind == "int" and not olive else 1)
     y = antq.fakequant(x, alpha, cb, True, ovp=olive)
     yf = antq.fakequant(x, alpha, cb, True, ovp=olive, flags=_lib.FLAG_FORCE_FLAT)
     assert torch.equal(y.view(torch.int16), yf.view(torch.int16)), "stream kernel != flat kernel"

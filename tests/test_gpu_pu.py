@@ -244,7 +244,8 @@ def test_default_plans(antq):
     assert plan(orc.ant_grid("flint", 4, False), False) == 4
     assert plan(orc.ant_grid("flint", 6, False), False) == 4
     assert plan(orc.ant_grid("flint", 4, True), True) == 1
-    assert plan(orc.ant_grid("int", 4, True), True) == 1
+    assert plan(orc.ant_grid("int", 4, True), True) == 4                  # uniform grid, per-row scales: the closed form
+    assert plan(orc.ant_grid("int", 4, True), False, t=x.view(1, -1)) == 1
     assert plan(orc.olive_grid("flint", 4, True), True, orc.olive_outlier_grid(4, True), True) == 1
     assert plan(orc.ant_grid("int", 8, True), True, t=x.view(-1, 64)) == 5
     assert plan(orc.ant_grid("apot", 4, False), True, t=x.view(-1, 64)) == 3
