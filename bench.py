@@ -368,12 +368,13 @@ def run_extras(torch, antq, dist, device, rank, world, local, graph, cb, peak):
         ev1.record()
         torch.cuda.synchronize()
         ms = reduce_max(ev0.elapsed_time(ev1)) / k
-        act_elems = 3 * S * H + S * H + S * H + S * 16384
+        # q / k / v quantize the same tensor with identical quantizers: one shared launch (antq/quantizer.py), so 1 + 1 + 1 + ffn
+        act_elems = S * H + S * H + S * H + S * 16384
         ex["opt_layer_batch_shard"] = {"ms_per_step": round(ms, 3), "tokens_per_s": round(world * S / (ms * 1e-3), 1),
                                        "samples_per_step": world, "fake_quant_bytes_per_rank_per_step": act_elems * 4,
                                        "collectives": "scatter(inputs, src=0) + all_gather(outputs)" if dist is not None else "none (1 GPU)",
                                        "note": "OPT-6.7B decoder layer (h 4096, ffn 16384), seq 2048, fp16, OliVe 4-bit W+A via quantize_model; "
-                                               "eval-mode weight cache on; one sample per rank"}
+                                               "eval-mode weight cache on; one sample per rank; the q / k / v input quantizers share one launch"}
         del q, layer
     except Exception as e:
         ex["opt_layer_batch_shard"] = {"error": repr(e)[:300]}

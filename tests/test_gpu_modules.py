@@ -287,6 +287,81 @@ RESULT.update(outs)
 
 
 @pytest.mark.parametrize("tree", ["ant", "olive"])
+def test_identical_input_quantizers_share_one_launch(tree):
+    """q / k / v projections quantize the same tensor with identically calibrated quantizers: in no-grad mode they share
+    one launch (same result bit for bit); a new forward pass, a changed input, different parameters or grad mode launch
+    again; the sharing survives CUDA-graph capture."""
+    res, _ = run(tree, r'''
+import antq.quantizer as Q
+from antq import ops
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+mode = "ant-int-flint"
+lin = [LinearQuantizer(mode=mode, wbit=4, abit=4, args=mkargs(mode)) for _ in range(4)]
+for i, l in enumerate(lin):
+    l.set_param(nn.Linear(256, 256).half())
+    l.to(dev).eval()
+    l.quant_weight.enable_quantization("w%d" % i); l.quant_input.enable_quantization("a%d" % i)
+calls = [0]
+real = ops.fakequant
+def counting(*a, **k):
+    calls[0] += 1
+    return real(*a, **k)
+ops.fakequant = counting
+x = torch.randn(64, 256, device=dev).half()
+x2 = (torch.randn(64, 256, device=dev) * 3).half()
+with torch.no_grad():
+    for l in lin[:3]:
+        l(x)                                            # calibration (q, k, v see the same data)
+    lin[3](x2)                                          # a fourth layer calibrated on other data: other alpha
+    def fwd(inp):
+        return [l(inp) for l in lin]
+    Q.SHARE_INPUT_QUANT = False
+    ref = fwd(x)
+    Q.SHARE_INPUT_QUANT = True
+    calls[0] = 0
+    got = fwd(x)
+    n_first = calls[0]                                  # activation launches: one shared by q / k / v + one for the fourth
+    calls[0] = 0
+    got2 = fwd(x)                                       # a new pass over the same tensor launches again
+    n_second = calls[0]
+    x.mul_(1.0)                                         # version bump: no stale hit
+    calls[0] = 0
+    got3 = fwd(x)
+    n_third = calls[0]
+    same = all(torch.equal(a, b) for a, b in zip(ref, got)) and all(torch.equal(a, b) for a, b in zip(ref, got2)) \
+        and all(torch.equal(a, b) for a, b in zip(ref, got3))
+    # CUDA graph: warm-up, capture, replay on new data
+    sx = x.clone()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fwd(sx)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        sy = fwd(sx)
+    sx.copy_(x2)
+    g.replay()
+    torch.cuda.synchronize()
+    Q.SHARE_INPUT_QUANT = False
+    ref2 = fwd(x2)
+    graph_ok = all(torch.equal(a, b) for a, b in zip(ref2, sy))
+with torch.enable_grad():
+    Q.SHARE_INPUT_QUANT = True
+    calls[0] = 0
+    xg = x.clone().requires_grad_(True)
+    for l in lin[:3]:
+        l.train(); l(xg)
+    n_grad = calls[0]
+ops.fakequant = real
+RESULT.update(dict(same=bool(same), n_first=n_first, n_second=n_second, n_third=n_third, graph_ok=bool(graph_ok), n_grad=n_grad))
+''', timeout=600)
+    # per pass: 4 weights are cached (eval) -> only activation launches are counted after the first pass fills the caches
+    assert res["same"] and res["graph_ok"], res
+    assert res["n_second"] == 2 and res["n_third"] == 2, res
+
+
+@pytest.mark.parametrize("tree", ["ant", "olive"])
 def test_weight_cache_as_packed_codes(tree):
     """antq.layers.CACHE_FORMAT = "codes": the eval-mode weight cache holds 0.5 byte per element + alpha and decodes on
     every forward -- outputs bit-identical to the fp-tensor cache and to no cache at all (conv and linear, OliVe pairs)."""

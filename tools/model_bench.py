@@ -101,15 +101,22 @@ def graphed(fn):
     return g.replay
 
 
-def quant_bytes(qmodel, per_forward_weights):
-    """Algorithmic bytes of one forward: every activation quantizer call, plus the weights if they are re-quantized."""
-    tot = [0]
-    hs = []
-    for m in qmodel.modules():
-        if isinstance(m, TensorQuantizer):  # noqa: F405
-            if m.is_input or per_forward_weights:
-                hs.append(m.register_forward_hook(lambda mod, inp, out: tot.__setitem__(0, tot[0] + 2 * inp[0].numel() * inp[0].element_size())))
-    return tot, hs
+class quant_bytes:
+    """Algorithmic bytes of one forward = sizeof(in) + sizeof(out) of every fake-quant LAUNCH (identical activation
+    quantizers fed the same tensor share one: antq/quantizer.py), counted by wrapping the op for one pass."""
+
+    def __init__(self, qmodel, per_forward_weights):
+        from antq import ops
+        self.ops, self.real, self.tot = ops, ops.fakequant, [0]
+
+        def counting(x, *a, **k):
+            self.tot[0] += 2 * x.numel() * x.element_size()
+            return self.real(x, *a, **k)
+        ops.fakequant = counting
+
+    def done(self):
+        self.ops.fakequant = self.real
+        return self.tot[0]
 
 
 def run(model, x, args, fused_ok, graph=True):
@@ -130,30 +137,28 @@ def run(model, x, args, fused_ok, graph=True):
                 if hasattr(m, "invalidate_weight_cache"):
                     m.invalidate_weight_cache()
             q(x)
-            tot, hs = quant_bytes(q, not cache)
+            qb = quant_bytes(q, not cache)
             q(x)
-            for h in hs:
-                h.remove()
+            tot = qb.done()
             ms = timeit(lambda: q(x))
             extra = ms - res["plain_ms"]
-            res[name] = {"forward_ms": round(ms, 3), "quant_bytes_per_forward": tot[0],
-                         "in_situ_GBps": round(tot[0] / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
-                         "frac_of_hbm_peak": round(tot[0] / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None}
+            res[name] = {"forward_ms": round(ms, 3), "quant_bytes_per_forward": tot,
+                         "in_situ_GBps": round(tot / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
+                         "frac_of_hbm_peak": round(tot / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None}
         L.CACHE_WEIGHTS, L.FUSED_LINEAR = True, False
         if graph:
             for m in q.modules():
                 if hasattr(m, "invalidate_weight_cache"):
                     m.invalidate_weight_cache()
             q(x)
-            tot, hs = quant_bytes(q, False)
+            qb = quant_bytes(q, False)
             q(x)
-            for h in hs:
-                h.remove()
+            tot = qb.done()
             ms = timeit(graphed(lambda: q(x)))
             extra = ms - res["cuda_graph"]["plain_ms"]
-            res["cuda_graph"].update({"weight_cache_ms": round(ms, 3), "quant_bytes_per_forward": tot[0],
-                                      "in_situ_GBps": round(tot[0] / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
-                                      "frac_of_hbm_peak": round(tot[0] / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None})
+            res["cuda_graph"].update({"weight_cache_ms": round(ms, 3), "quant_bytes_per_forward": tot,
+                                      "in_situ_GBps": round(tot / (extra * 1e-3) / 1e9, 1) if extra > 0 else None,
+                                      "frac_of_hbm_peak": round(tot / (extra * 1e-3) / 1e9 / PEAK, 3) if extra > 0 else None})
     res["plain_ms"] = round(res["plain_ms"], 3)
     return res
 
