@@ -120,9 +120,10 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     const bool ovp2_fast = ovp && info && (info->flags & ANTQ_CB_SYMMETRIC) && nt <= 15;
     // fp32 I/O: the chain works on one element per register there (no packed pairs) and loses to the closed form even at 7
     // thresholds (31.3 vs 25.5 us per 4096^2, flint-4 signed)
-    const bool f32_pu = dtype == ANTQ_F32 && pu && !ovp && long_rows;
+    // (OliVe pairs included: its fp32 chain runs at 57-68 us, the closed form + pair logic at 26.5)
+    const bool f32_pu = dtype == ANTQ_F32 && pu && long_rows;
     // bf16 I/O, uniform grids (int-k): 14.7 / 13.7 us (per-row / per-tensor) against the chain's 18.2 / 15.8
-    const bool bf16_pu = dtype == ANTQ_BF16 && pu && !ovp && long_rows && (info->flags & ANTQ_CB_PU_UNIFORM);
+    const bool bf16_pu = dtype == ANTQ_BF16 && pu && long_rows && (info->flags & ANTQ_CB_PU_UNIFORM);   // OliVe int: 14.8 vs 16.3
     // fp16 I/O, uniform grids, per-row scales: 13.7 us against the chain's 14.7 (its SYMX path: one extra compare per pair);
     // with one scale the chain keeps a small edge (13.3 vs 13.6)
     const bool f16_int_pu = dtype == ANTQ_F16 && pu && !ovp && long_rows && rows > 1 && (info->flags & ANTQ_CB_PU_UNIFORM);
