@@ -235,6 +235,33 @@ def test_pu_olive_random(antq, kind, signed, dtype):
         assert_bit_equal(to_np(yt), reft, "olive closed form per-tensor")
 
 
+@pytest.mark.parametrize("signed", [True, False])
+def test_pu_olive_8bit_default_plan(antq, signed):
+    """OliVe with 8-bit codebooks (255 + 254 entries signed: far beyond any compare chain) takes the closed form on its
+    int-8 normal levels and the pair logic (rank search over ~500 thresholds) where an outlier sits."""
+    rng = np.random.default_rng(8)
+    grid, outl = orc.olive_int_grid(8, signed), orc.olive_outlier_grid(8, signed)
+    cb = _cb(antq, grid, outl)
+    from antq import _lib
+    assert cb.info.flags & _lib.CB_PU_OVP
+    rows, cols = 24, 4096
+    x = (rng.standard_normal((rows, cols)) * 0.02).astype(np.float32)
+    x[rng.random((rows, cols)) < 0.004] *= 14
+    x[5, 9], x[7] = np.nan, 0.0
+    if not signed:
+        x = np.abs(x)
+    x = x.astype(np.float16)
+    alpha = (3.0 * np.nanstd(x.astype(np.float32), axis=1) * rng.uniform(0.8, 1.2, rows)).astype(np.float32)
+    xd, ad = torch.from_numpy(x).to(dev()), torch.from_numpy(alpha).to(dev())
+    assert antq.fakequant_plan(xd, cb, True, ovp=True) == 4
+    ref = orc.olive_forward(x, alpha, grid, outl, per_row=True)
+    assert_bit_equal(to_np(antq.fakequant(xd, ad, cb, True, ovp=True)), ref, "olive 8-bit, default plan")
+    a0 = np.float32(0.06)
+    reft = orc.olive_forward(x.reshape(-1), a0, grid, outl, per_row=False)
+    yt = antq.fakequant(xd.view(-1), torch.tensor([a0], device=dev()), cb, False, ovp=True)
+    assert_bit_equal(to_np(yt), reft, "olive 8-bit per-tensor")
+
+
 def test_default_plans(antq):
     """What a model actually hits: 8-bit int weights and post-ReLU 4-bit activations take the closed form, signed 4-bit
     keeps the chain, OliVe keeps its two-phase chain."""
