@@ -835,6 +835,96 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
 }
 
 // ==================================================================================================
+// Rows of ONE or TWO vectors (group-8 / group-16 scales in 16-bit data): every vector (pair) has its own scale, so the
+// per-row constants are the bottleneck -- the x-space window and clamp bounds of the kernels above cost ~30 instructions
+// per row.  Here a row costs its scale (one IEEE division), a reciprocal and a validity select; the clamp and the window
+// test move to t-space, where their bounds are constants of the codebook (two FMNMX per element, one FMNMX3 tree per
+// vector).  Same tile structure (four loads in flight per lane), no row table.
+// ==================================================================================================
+template <typename T, bool UNIFORM>
+__global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_lean_kernel(const PuParams p) {
+    typedef AntqType<T> A;
+    constexpr int VEC = A::kVec;
+    __shared__ float2 tab[UNIFORM ? 1 : 512];
+    __shared__ float x_thr[ANTQ_MAX_GRID], x_lev[ANTQ_MAX_GRID];
+    if (!UNIFORM) {
+        for (int i = threadIdx.x; i < 512; i += kShortThreads) tab[i] = p.cb->pu_tab[i & 255];
+    }
+    PuExact X;
+    X.thr = x_thr; X.lev = x_lev; X.nlev = p.cb->n_levels;
+    X.win = (p.cb->flags & ANTQ_CB_WELLSEP) ? p.cb->lim_idx : -1.0f;
+    for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
+    __syncthreads();
+    const PuK K = pu_load_k(p.cb, p.lim, 0);
+    const float tlim = __fmul_rn(__fmul_rn(K.lim, K.inv_c), 0.9990234375f);   // |t| <= tlim: inside the exact window
+    const float nan = __int_as_float(0x7fc00000);
+    const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
+    uint4 *xout = reinterpret_cast<uint4 *>(p.out);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned ntiles = (p.nvec + kTileVec - 1) / kTileVec;
+    const unsigned nwarps = gridDim.x * kShortWarps;
+    for (unsigned t = blockIdx.x * kShortWarps + warp; t < ntiles; t += nwarps) {
+        const unsigned v0 = t * kTileVec;
+        const unsigned vend = min(v0 + kTileVec, p.nvec);
+        uint4 raw[kVPL];
+        float al[kVPL];
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            raw[j] = make_uint4(0, 0, 0, 0);
+            al[j] = 0.0f;
+            if (v < vend) {
+                raw[j] = antq_ldg_stream(xin + v);
+                al[j] = __ldg(p.alpha + (p.alpha_per_row ? v >> p.cols_shift : 0u));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kVPL; j++) {
+            const unsigned v = v0 + j * 32 + lane;
+            if (v >= vend) break;
+            const float s = __fdiv_rn(al[j], p.gmax);
+            float rs;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+            float kx = __fmul_rn(rs, K.inv_c);
+            kx = (kx > 0.0f && kx < __int_as_float(0x7f800000)) ? kx : nan;   // bad scale: every t is NaN -> wild
+            float f[VEC], o[VEC];
+            PuIO<T>::unpack(raw[j], f);
+            float rmax = 0.0f;
+            bool near = false, is_wild = false;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const float t_ = __fmul_rn(f[e], kx);
+                is_wild |= !(fabsf(t_) <= tlim);                      // outside the exact window, NaN, Inf, bad scale
+                const float tc = fminf(fmaxf(t_, K.xc_lo), K.xc_hi);  // (a NaN becomes xc_lo here: that vector is wild anyway)
+                float M = 12582912.0f;
+                if (!UNIFORM) M = tab[__float_as_uint(tc) >> 23].x;
+                const float mf = __fsub_rn(__fadd_rn(tc, M), M);
+                const float rr = fabsf(__fsub_rn(tc, mf));
+                if (UNIFORM) rmax = fmaxf(rmax, rr);
+                else near |= rr >= tab[__float_as_uint(tc) >> 23].y;
+                o[e] = __fmul_rn(__fmul_rn(mf, K.c), s);              // tc was clamped: mf is in [kmin, kmax]
+            }
+            if (UNIFORM) near = rmax >= K.hd_c;
+            uint4 q = PuIO<T>::pack(o);
+            if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], s, kx, K, tab);   // in-window elements settled; wild ones rewritten below
+            antq_stg_stream(xout + v, q);
+            if (is_wild) {
+                const PuRow r = pu_row<T>(al[j], p, K, true);
+                pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+            }
+        }
+    }
+}
+
+template <typename T, bool UNIFORM> int launch_lean(const PuParams &p, cudaStream_t st) {
+    const long long tiles = ((long long)p.nvec + kTileVec - 1) / kTileVec;
+    const long long want = (tiles + kShortWarps - 1) / kShortWarps;
+    const long long cap = (long long)antq_num_sms() * kShortCtas;
+    antq_pu_lean_kernel<T, UNIFORM><<<(int)(want < cap ? want : cap), kShortThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// ==================================================================================================
 // Dynamic scale groups: alpha = max|x| over the group * ratio, computed in the same pass (ONE read of x).
 // A group of cols = L * VEC elements is held by L adjacent lanes (L a power of two <= 32): local abs-max, xor-shuffle
 // reduction (integer max on the fp32 bit patterns of |x|: NaN-propagating, like torch's abs().max()), then the closed form.
@@ -1164,6 +1254,14 @@ int antq_launch_pu_short(const void *x, void *out, const float *alpha, int alpha
             case ANTQ_BF16: return xc ? ANTQ_PU_GO(__nv_bfloat16, true) : ANTQ_PU_GO(__nv_bfloat16, false);
         }
 #undef ANTQ_PU_GO
+        return ANTQ_EINVAL;
+    }
+    if (p.alpha_per_row && p.cols_vec <= 2 && !(dbg & 16)) {          // one or two vectors per row: the lean kernel (at four: 18.8 vs 17.5 us)
+        switch (dtype) {
+            case ANTQ_F32: return uni ? launch_lean<float, true>(p, st) : launch_lean<float, false>(p, st);
+            case ANTQ_F16: return uni ? launch_lean<__half, true>(p, st) : launch_lean<__half, false>(p, st);
+            case ANTQ_BF16: return uni ? launch_lean<__nv_bfloat16, true>(p, st) : launch_lean<__nv_bfloat16, false>(p, st);
+        }
         return ANTQ_EINVAL;
     }
 #define ANTQ_PU_GO(T, X) (uni ? launch_short<T, true, X>(p, st) : launch_short<T, false, X>(p, st))
