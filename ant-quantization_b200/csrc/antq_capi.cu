@@ -47,7 +47,7 @@ extern "C" {
 int antq_abi_version(void) { return ANTQ_ABI_VERSION; }
 
 const char *antq_build_info(void) {
-    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_pu_stream_kernel antq_pu_short_kernel antq_pu_dynamic_kernel "
+    return "libantq sm_100a; kernels: antq_prepare_kernel antq_stream_kernel antq_pu_stream_kernel antq_pu_short_kernel antq_pu_lean_kernel antq_pu_dynamic_kernel "
            "antq_pu_encode_kernel antq_short_kernel antq_flat_kernel antq_absmax_kernel antq_mse_sweep_kernel antq_calib_score_kernel "
            "antq_encode_p4_kernel antq_decode_p4_kernel antq_decode_p4_fast_kernel antq_bwd_kernel antq_linear_p4_kernel "
            "antq_levels_e4m3_kernel; built " __DATE__;

@@ -28,7 +28,8 @@
 //   antq_pu_short_kernel    shorter rows and scale groups (group-8/16/32, 1x1-conv weights): a warp owns a tile of 128
 //                           vectors, issues its loads first, computes the tile's row constants once (one row per lane,
 //                           shared through shared memory) and then runs the closed form.
-//   antq_pu_dynamic_kernel  the same with alpha = max|x| * ratio of each group computed in the kernel (one read of x).
+//   antq_pu_lean_kernel     rows of one or two vectors (group-8 / 16): window and clamp in t-space, a row costs one division.
+//   antq_pu_dynamic_kernel  the tile kernel with alpha = max|x| * ratio of each group computed in the kernel (one read of x).
 // Bound: HBM for uniform grids (12.75 instructions per element: the chain kernel's plateau); the per-octave-table grids
 // (15.7 instructions per element) are issue-bound at ~0.65 of the HBM rate (measured: profiles/r02_notes.md).
 #include <stdio.h>
