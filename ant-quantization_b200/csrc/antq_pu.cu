@@ -842,6 +842,46 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
 // test move to t-space, where their bounds are constants of the codebook (two FMNMX per element, one FMNMX3 tree per
 // vector).  Same tile structure (four loads in flight per lane), no row table.
 // ==================================================================================================
+// One vector of a row that has (nearly) no other vectors to share constants with: scale, reciprocal, validity; clamp and
+// window in t-space (constants of the codebook); near-midpoint vectors settled by the two-candidate decision, wild ones
+// (outside the window, NaN, Inf, bad scale) literally.
+template <typename T, bool UNIFORM>
+__device__ __forceinline__ void pu_lean_vec(const uint4 raw, const float alpha, const PuParams &p, const PuK &K, const float tlim,
+                                            const float2 *tab, const PuExact &X, uint4 *dstv, T *dste) {
+    constexpr int VEC = PuIO<T>::VEC;
+    const float nan = __int_as_float(0x7fc00000);
+    const float s = __fdiv_rn(alpha, p.gmax);
+    float rs;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+    float kx = __fmul_rn(rs, K.inv_c);
+    kx = (kx > 0.0f && kx < __int_as_float(0x7f800000)) ? kx : nan;   // bad scale: every t is NaN -> wild
+    float f[VEC], o[VEC];
+    PuIO<T>::unpack(raw, f);
+    float rmax = 0.0f;
+    bool near = false, is_wild = false;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) {
+        const float t_ = __fmul_rn(f[e], kx);
+        is_wild |= !(fabsf(t_) <= tlim);                      // outside the exact window, NaN, Inf, bad scale
+        const float tc = fminf(fmaxf(t_, K.xc_lo), K.xc_hi);  // (a NaN becomes xc_lo here: that vector is wild anyway)
+        float M = 12582912.0f;
+        if (!UNIFORM) M = tab[__float_as_uint(tc) >> 23].x;
+        const float mf = __fsub_rn(__fadd_rn(tc, M), M);
+        const float rr = fabsf(__fsub_rn(tc, mf));
+        if (UNIFORM) rmax = fmaxf(rmax, rr);
+        else near |= rr >= tab[__float_as_uint(tc) >> 23].y;
+        o[e] = __fmul_rn(__fmul_rn(mf, K.c), s);              // tc was clamped: mf is in [kmin, kmax]
+    }
+    if (UNIFORM) near = rmax >= K.hd_c;
+    uint4 q = PuIO<T>::pack(o);
+    if (near) q = pu_vec_exact<T, UNIFORM>(raw, s, kx, K, tab);   // in-window elements settled; wild ones rewritten below
+    antq_stg_stream(dstv, q);
+    if (is_wild) {
+        const PuRow r = pu_row<T>(alpha, p, K, true);
+        pu_redo_vec<T, UNIFORM>(p.cb, X, raw, r, K, tab, dste);
+    }
+}
+
 template <typename T, bool UNIFORM>
 __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_lean_kernel(const PuParams p) {
     typedef AntqType<T> A;
@@ -858,7 +898,6 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_lean_kernel
     __syncthreads();
     const PuK K = pu_load_k(p.cb, p.lim, 0);
     const float tlim = __fmul_rn(__fmul_rn(K.lim, K.inv_c), 0.9990234375f);   // |t| <= tlim: inside the exact window
-    const float nan = __int_as_float(0x7fc00000);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -883,36 +922,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_lean_kernel
         for (int j = 0; j < kVPL; j++) {
             const unsigned v = v0 + j * 32 + lane;
             if (v >= vend) break;
-            const float s = __fdiv_rn(al[j], p.gmax);
-            float rs;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
-            float kx = __fmul_rn(rs, K.inv_c);
-            kx = (kx > 0.0f && kx < __int_as_float(0x7f800000)) ? kx : nan;   // bad scale: every t is NaN -> wild
-            float f[VEC], o[VEC];
-            PuIO<T>::unpack(raw[j], f);
-            float rmax = 0.0f;
-            bool near = false, is_wild = false;
-#pragma unroll
-            for (int e = 0; e < VEC; e++) {
-                const float t_ = __fmul_rn(f[e], kx);
-                is_wild |= !(fabsf(t_) <= tlim);                      // outside the exact window, NaN, Inf, bad scale
-                const float tc = fminf(fmaxf(t_, K.xc_lo), K.xc_hi);  // (a NaN becomes xc_lo here: that vector is wild anyway)
-                float M = 12582912.0f;
-                if (!UNIFORM) M = tab[__float_as_uint(tc) >> 23].x;
-                const float mf = __fsub_rn(__fadd_rn(tc, M), M);
-                const float rr = fabsf(__fsub_rn(tc, mf));
-                if (UNIFORM) rmax = fmaxf(rmax, rr);
-                else near |= rr >= tab[__float_as_uint(tc) >> 23].y;
-                o[e] = __fmul_rn(__fmul_rn(mf, K.c), s);              // tc was clamped: mf is in [kmin, kmax]
-            }
-            if (UNIFORM) near = rmax >= K.hd_c;
-            uint4 q = PuIO<T>::pack(o);
-            if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], s, kx, K, tab);   // in-window elements settled; wild ones rewritten below
-            antq_stg_stream(xout + v, q);
-            if (is_wild) {
-                const PuRow r = pu_row<T>(al[j], p, K, true);
-                pu_redo_vec<T, UNIFORM>(p.cb, X, raw[j], r, K, tab, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
-            }
+            pu_lean_vec<T, UNIFORM>(raw[j], al[j], p, K, tlim, tab, X, xout + v, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
         }
     }
 }
@@ -946,6 +956,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
     for (int i = threadIdx.x; i < X.nlev; i += kShortThreads) { x_thr[i] = p.cb->thr[i]; x_lev[i] = p.cb->level[i]; }
     __syncthreads();
     const PuK K = pu_load_k(p.cb, p.lim, p.ovp);
+    const float tlim = __fmul_rn(__fmul_rn(K.lim, K.inv_c), 0.9990234375f);
     const uint4 *xin = reinterpret_cast<const uint4 *>(p.x);
     uint4 *xout = reinterpret_cast<uint4 *>(p.out);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -983,6 +994,18 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
                 m = u > m ? u : m;
             }
             am[j] = __fmul_rn(__uint_as_float(m), ratio);             // alpha = absmax * ratio (fp32, like the torch expression)
+        }
+        if (L <= 2u) {
+            // one or two vectors per group: no row table, the lean arithmetic (see antq_pu_lean_kernel)
+#pragma unroll
+            for (int j = 0; j < kVPL; j++) {
+                const unsigned v = v0 + j * 32 + lane;
+                if (v < vend) {
+                    if (alpha_out && (v & (L - 1u)) == 0) alpha_out[v >> sh] = am[j];
+                    pu_lean_vec<T, UNIFORM>(raw[j], am[j], p, K, tlim, tab, X, xout + v, reinterpret_cast<T *>(p.out) + (long long)v * VEC);
+                }
+            }
+            continue;
         }
         const unsigned row0 = v0 >> sh, nrows = (vend - v0) >> sh;    // groups of this tile: <= kTileVec / L
         for (unsigned k = 0; k * 32u < nrows; k++) {
