@@ -126,7 +126,8 @@ int antq_fakequant_plan(const antq_codebook_info *info, int64_t rows, int64_t co
     const bool bf16_pu = dtype == ANTQ_BF16 && pu && long_rows && (info->flags & ANTQ_CB_PU_UNIFORM);   // OliVe int: 14.8 vs 16.3
     // fp16 I/O, uniform grids, per-row scales: 13.7 us against the chain's 14.7 (its SYMX path: one extra compare per pair);
     // with one scale the chain keeps a small edge (13.3 vs 13.6)
-    const bool f16_int_pu = dtype == ANTQ_F16 && pu && !ovp && long_rows && rows > 1 && (info->flags & ANTQ_CB_PU_UNIFORM);
+    // (int-3 and below: 3 thresholds, the chain stays -- 13.0 vs 13.9 us)
+    const bool f16_int_pu = dtype == ANTQ_F16 && pu && !ovp && long_rows && rows > 1 && nt >= 6 && (info->flags & ANTQ_CB_PU_UNIFORM);
     if (chain && (nt <= 7 || !pu || ovp2_fast) && !f32_pu && !bf16_pu && !f16_int_pu) return 1;
     if (pu && long_rows) return 4;
     if (chain) return 1;
