@@ -331,6 +331,40 @@ __device__ __noinline__ uint4 pu_vec_exact(const uint4 raw, const float s, const
     return PuIO<T>::pack(o);
 }
 
+// Near-midpoint repair of a vector the fast path has already quantized (`q`): only the flagged ELEMENTS are settled by the
+// two-candidate decision (one division each) instead of all VEC.  In the tile kernels a rare per-lane event is a frequent
+// per-warp one (int-8: 0.4-0.8 % of the vectors, i.e. every 5th to 8th warp iteration), so what it costs matters: ~90
+// instructions here against ~350 for pu_vec_exact.  The flags are recomputed with the most conservative margin of the
+// fast paths (a superset of theirs; the decision is valid for every in-window element).
+template <typename T, bool UNIFORM>
+__device__ __noinline__ uint4 pu_vec_fix_near(const uint4 raw, const uint4 q, const float s, const float kx, const PuK K, const float2 *tab) {
+    constexpr int VEC = PuIO<T>::VEC;
+    float f[VEC];
+    PuIO<T>::unpack(raw, f);
+    T o[VEC];
+    *reinterpret_cast<uint4 *>(o) = q;
+    unsigned m = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) {
+        const float tc = fminf(fmaxf(__fmul_rn(f[e], kx), K.xc_lo), K.xc_hi);
+        float M = 12582912.0f, hd = K.hd_c;
+        if (!UNIFORM) { const float2 md = tab[__float_as_uint(tc) >> 23]; M = md.x; hd = md.y; }
+        const float mf = __fsub_rn(__fadd_rn(tc, M), M);
+        m |= (fabsf(__fsub_rn(tc, mf)) >= hd ? 1u : 0u) << e;
+    }
+    while (m) {
+        const int e = __ffs(m) - 1;
+        m &= m - 1;
+        float xf = f[0];
+#pragma unroll
+        for (int i = 1; i < VEC; i++) xf = e == i ? f[i] : xf;
+        const T val = AntqType<T>::from_f32_rn(pu_elem_exact<UNIFORM>(xf, s, kx, K, tab));
+#pragma unroll
+        for (int i = 0; i < VEC; i++) o[i] = e == i ? val : o[i];
+    }
+    return *reinterpret_cast<const uint4 *>(o);
+}
+
 // Which elements of a vector need the literal path (bit e): those outside the exact window (NaN and Inf included).
 template <typename T, bool UNIFORM>
 __device__ __forceinline__ unsigned pu_vec_mask(const uint4 raw, const PuRow &r, const PuK &K, const float2 *tab) {
@@ -823,7 +857,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_short_kerne
                 PuRow r = pu_row_unpack<T>(rs[pu_row_local(p, tr, v)]);
                 bool near, wild;
                 uint4 q = pu_vec<T, UNIFORM, XC>(raw[j], r, K, tab, near, wild);
-                if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
+                if (near) q = pu_vec_fix_near<T, UNIFORM>(raw[j], q, r.s, r.kx, K, tab);
                 antq_stg_stream(xout + v, q);
                 if (wild) {
                     if (sizeof(T) == 2) r.xl = pu_row_xl(K, r.s);
@@ -874,7 +908,7 @@ __device__ __forceinline__ void pu_lean_vec(const uint4 raw, const float alpha, 
     }
     if (UNIFORM) near = rmax >= K.hd_c;
     uint4 q = PuIO<T>::pack(o);
-    if (near) q = pu_vec_exact<T, UNIFORM>(raw, s, kx, K, tab);   // in-window elements settled; wild ones rewritten below
+    if (near) q = pu_vec_fix_near<T, UNIFORM>(raw, q, s, kx, K, tab);   // in-window elements settled; wild ones rewritten below
     antq_stg_stream(dstv, q);
     if (is_wild) {
         const PuRow r = pu_row<T>(alpha, p, K, true);
@@ -1030,7 +1064,7 @@ __global__ void __launch_bounds__(kShortThreads, kShortCtas) antq_pu_dynamic_ker
                 PuRow r = pu_row_unpack<T>(rs[(v - v0) >> sh]);
                 bool near, wild;
                 uint4 q = pu_vec<T, UNIFORM, XC>(raw[j], r, K, tab, near, wild);
-                if (near) q = pu_vec_exact<T, UNIFORM>(raw[j], r.s, r.kx, K, tab);
+                if (near) q = pu_vec_fix_near<T, UNIFORM>(raw[j], q, r.s, r.kx, K, tab);
                 antq_stg_stream(xout + v, q);
                 if (wild) {
                     if (sizeof(T) == 2) r.xl = pu_row_xl(K, r.s);
