@@ -40,3 +40,22 @@ for name, h in (("torch_pin_memory()", hb), ("torch_empty(pin_memory=True)", hb2
         e1.record(); torch.cuda.synchronize()
         out["%s %s" % (name, kind)] = round(10 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
 print(json.dumps(out))
+# both directions at once, on two streams (the full-duplex rate the e2e leg can hope for)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True); h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+d_in = torch.empty(n, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+for chunk in (n, 16 << 20):
+    def both():
+        for off in range(0, n, chunk):
+            with torch.cuda.stream(s1):
+                d_in[off:off + chunk].copy_(h_in[off:off + chunk], non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out[off:off + chunk].copy_(d_out[off:off + chunk], non_blocking=True)
+    both(); torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(10):
+        both()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"both_directions_chunk_MiB": chunk >> 20, "GBps_each_way": round(10 * n / dt / 1e9, 1), "GBps_total": round(20 * n / dt / 1e9, 1)}))
