@@ -67,6 +67,11 @@ def test_pu_exhaustive_fp16(antq, kind, bit, signed):
     assert antq.fakequant_plan(torch.from_numpy(xs).to(dev()), cb, True, flags=_lib.FLAG_FORCE_PU) == 5
     ys = _run(antq, xs, np.repeat(alpha, 65536 // 64), cb, True, _lib.FLAG_FORCE_PU)
     assert_bit_equal(to_np(ys).reshape(x.shape), ref, "short")
+    # rows of one and two vectors: the lean kernel (window and clamp in t-space)
+    for g in (8, 16):
+        xl = x.reshape(-1, g)
+        yl = _run(antq, xl, np.repeat(alpha, 65536 // g), cb, True, 0)
+        assert_bit_equal(to_np(yl).reshape(x.shape), ref, "lean g=%d" % g)
 
 
 @pytest.mark.parametrize("dtype", ["f32", "f16", "bf16"])
