@@ -90,11 +90,14 @@ def _rz16(v):
     return h
 
 
-def forward(x, s, pu, lim, exact, out_dtype, xclamp=False, pair_all=False):
+def forward(x, s, pu, lim, exact, out_dtype, xclamp=False, pair_all=False, lean=False):
     """x: array of out_dtype; s: fp32 scale (alpha / max(grid)); lim: the codebook's exact window in d-space.
     `exact(xs)` is the literal reference arithmetic for the flagged elements.  Returns (out, flagged).
     xclamp (fp16 inputs, grids with pu["xc16"]): the clamp to [kmin, kmax] is applied to the INPUT with bounds rounded
-    toward zero to fp16, as the kernel does with two packed min / max per pair, and t is not clamped afterwards."""
+    toward zero to fp16, as the kernel does with two packed min / max per pair, and t is not clamped afterwards.
+    lean (antq_pu_lean_kernel, rows of one or two vectors): the clamp and the window test are done on t with constants of
+    the codebook -- t clamped to [xc_lo, xc_hi], uniform grids flag |r| >= 0.5 - (max|k| + 1) 2^-19, in-window means
+    |t| <= lim / c * 0.999 -- and the reciprocal of the scale is the approximate one (<= 1 ulp off)."""
     s = f32(s)
     xf = x.astype(f32)
     with np.errstate(all="ignore"):
@@ -108,6 +111,9 @@ def forward(x, s, pu, lim, exact, out_dtype, xclamp=False, pair_all=False):
             xh = np.where(np.isnan(xh), lo, np.maximum(xh, lo))          # hmax2 / hmin2 return the non-NaN operand
             xq = np.minimum(xh, hi).astype(f32)
         t = (xq * kx).astype(f32)
+        if lean:
+            t_raw = t
+            t = np.minimum(np.maximum(np.where(np.isnan(t), pu["xc_lo"], t), pu["xc_lo"]), pu["xc_hi"]).astype(f32)
         E = (_bits(t) >> 23) & 0xff
         M = pu["magic"][E]
         dl = pu["delta"][E]
@@ -115,11 +121,17 @@ def forward(x, s, pu, lim, exact, out_dtype, xclamp=False, pair_all=False):
         r = (t - mf).astype(f32)
         h = (_bits(M) - np.uint32((24 << 23) | 0x400000)).view(f32)
         near = np.abs(r) >= (h - dl).astype(f32)                  # |r| <= h always: "within delta of a midpoint"
-        mfc = mf if xclamp else np.minimum(np.maximum(mf, pu["kmin"]), pu["kmax"]).astype(f32)
+        if lean and pu["uniform"]:
+            hd_c = f32(f32(0.5) - f32(f32(max(float(pu["kmax"]), -float(pu["kmin"])) + 1.0) * f32(2.0 ** -19)))
+            near = np.abs(r) >= hd_c
+        mfc = mf if (xclamp or lean) else np.minimum(np.maximum(mf, pu["kmin"]), pu["kmax"]).astype(f32)
         q = (mfc * pu["c"]).astype(f32)
         o = (q * s).astype(f32)
         xl = f32(f32(f32(lim) * s) * f32(0.9990234375))
         window = np.abs(xf) <= xl                                 # False for NaN
+        if lean:
+            tlim = f32(f32(f32(lim) * pu["inv_c"]) * f32(0.9990234375))
+            window = np.abs(t_raw) <= tlim
         row_ok = bool(s > 0) and bool(np.isfinite(s)) and bool(np.isfinite(kx)) and bool(kx > 0)
         # pu_vec_exact: the pair decision, from the UNCLAMPED input
         tp = (xf * kx).astype(f32)

@@ -72,6 +72,10 @@ def test_fp16_exhaustive(kind, bit, signed):
         got3, _ = pm.forward(ALL_F16, s_eff, pu, lim_of(cb), exact, np.float16, pair_all=True)
         same = (got3.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got3) & np.isnan(ref))
         assert same.all(), ("pair", kind, bit, signed, s, ALL_F16[~same][:5], got3[~same][:5], ref[~same][:5])
+        # the lean variant (clamp and window on t, constant near margin for uniform grids)
+        got4, _ = pm.forward(ALL_F16, s_eff, pu, lim_of(cb), exact, np.float16, lean=True)
+        same = (got4.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got4) & np.isnan(ref))
+        assert same.all(), ("lean", kind, bit, signed, s, ALL_F16[~same][:5], got4[~same][:5], ref[~same][:5])
         inwin = np.abs(ALL_F16.astype(f32)) <= f32(lim_of(cb) * s_eff) * f32(0.99)
         flagged += (fl & inwin).sum() / max(inwin.sum(), 1)
     assert flagged / len(scales(gmax, 6 if bit >= 7 else 10)) < 0.02          # the closed form is what runs
