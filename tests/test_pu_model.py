@@ -109,3 +109,40 @@ def test_fp32_threshold_huggers(kind, bit, signed):
         # WITHOUT the near-midpoint redo the closed form would be wrong somewhere among the huggers -> the test bites
     # sanity: the model really is exercised on its own (few flagged among the random part)
     assert fl[:30000].mean() < 0.01
+
+
+@pytest.mark.parametrize("kind,signed", [("flint", True), ("flint", False), ("int", True), ("int", False)])
+def test_olive_normal_levels_below_the_outlier_threshold(kind, signed):
+    """The OliVe closed-form path (ANTQ_CB_PU_OVP): grid + outliers is not piecewise uniform, but with the window cut at the
+    first outlier threshold every in-window element must quantize exactly as the reference's scan over the WHOLE codebook
+    does (element-wise: what a pair without an outlier gets), using only the normal levels' closed form."""
+    grid, outl = orc.olive_grid(kind, 4, signed), orc.olive_outlier_grid(4, signed)
+    whole = np.concatenate([grid, outl]).astype(f32)
+    cbw = xm.prepare_codebook(whole)
+    lev, thr = cbw["levels"], cbw["thr"]
+    normal = np.abs(lev) <= 32
+    lo, hi = int(np.argmax(normal)), int(len(lev) - 1 - np.argmax(normal[::-1]))
+    assert normal[lo:hi + 1].all()
+    tout = min(thr[hi] if hi < len(lev) - 1 else np.inf, -thr[lo - 1] if lo > 0 else np.inf)
+    pu = pm.analyze(lev[lo:hi + 1])
+    assert pu is not None
+    gmax = grid.max()
+    checked = 0
+    for s in scales(gmax, 8):
+        alpha = f32(s * gmax)
+        s_eff = f32(alpha / gmax)
+
+        def exact(xs):
+            # the reference's OliVe forward, each value paired with a zero (never an outlier, so the value itself is
+            # what the scan over grid + outliers gives at the scale alpha / max(normal grid))
+            z = np.zeros(2 * xs.size, dtype=xs.dtype)
+            z[::2] = xs
+            return orc.olive_forward(z, alpha, grid, outl, per_row=False)[::2]
+        lim = f32(min(float(lim_of(cbw)), float(tout)))
+        for kw in (dict(), dict(lean=True)) + ((dict(xclamp=True),) if pu["xc16"] else ()):
+            got, fl = pm.forward(ALL_F16, s_eff, pu, lim, exact, np.float16, **kw)
+            ref = exact(ALL_F16)
+            same = (got.view(np.uint16) == ref.view(np.uint16)) | (np.isnan(got) & np.isnan(ref))
+            assert same.all(), (kind, signed, s, kw, ALL_F16[~same][:5], got[~same][:5], ref[~same][:5])
+            checked += int((~fl).sum())
+    assert checked > 10000                                               # the closed form, not the fallback, was what ran
