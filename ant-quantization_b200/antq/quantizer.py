@@ -82,12 +82,13 @@ class QuantBase:
 # quantize the block's input, each with its own -- identically calibrated -- quantizer: the reference launches three times)
 # share one launch in no-grad mode.  The result is the same tensor bit for bit; ANTQ_SHARE_INPUT_QUANT=0 turns it off.
 SHARE_INPUT_QUANT = os.environ.get("ANTQ_SHARE_INPUT_QUANT", "1") != "0"
+_capturing = getattr(torch._C, "_cuda_isCurrentStreamCapturing", None) or torch.cuda.is_current_stream_capturing
 
 
 class Quantizer(nn.Module):
     flavor = "ant"
     _share_ids = {}                  # (grid, outliers, alpha, pairs) -> small int
-    _share_memo = None               # (x, x._version, share id, out, out._version, ids of the quantizers served)
+    _share_memo = None               # (x, x._version, share id, out, out._version, ids of the quantizers served, capturing?)
 
     def __init__(self, mode="base", bit=8, is_signed=True, is_enable=False, is_input=False, args=None, operator=None):
         super().__init__()
@@ -247,9 +248,12 @@ class Quantizer(nn.Module):
                 # A hit needs the same tensor OBJECT at the same version, the same parameters, an untouched result -- and a
                 # quantizer that has not used this entry yet: the same quantizer coming back means a new forward pass (or
                 # a CUDA-graph capture after its warm-up), which must launch again.
+                # ... and the same capture state: a result recorded while a CUDA graph was being captured has not been
+                # computed yet, and an eager result is not part of a graph being captured now.
                 m = Quantizer._share_memo
+                cap = _capturing()
                 if (m is not None and m[0] is x and m[1] == x._version and m[2] == sh[0] and m[4] == m[3]._version
-                        and id(self) not in m[5]):
+                        and id(self) not in m[5] and m[6] == cap):
                     m[5].add(id(self))
                     return m[3]
                 if x.is_contiguous():
@@ -257,7 +261,7 @@ class Quantizer(nn.Module):
                 else:
                     xc = x.contiguous()
                     out = ops.fakequant(xc, alpha, self._codebook(xc.device), self.is_perchannel, self._ovp).view(x.shape)
-                Quantizer._share_memo = (x, x._version, sh[0], out, out._version, {id(self)})
+                Quantizer._share_memo = (x, x._version, sh[0], out, out._version, {id(self)}, cap)
                 return out
         if x.is_contiguous():
             return ops.fakequant(x, alpha, self._codebook(x.device), self.is_perchannel, self._ovp)

@@ -343,9 +343,23 @@ with torch.no_grad():
     sx.copy_(x2)
     g.replay()
     torch.cuda.synchronize()
+    # a capture that starts with a quantizer OTHER than the one that last launched eagerly on the same tensor must not
+    # reuse the eager result (it is not part of the graph)
+    sx2 = x.clone()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        lin[1](sx2)
+    torch.cuda.current_stream().wait_stream(s)
+    lin[0](sx2)                                         # eager launch by q: the entry k could share
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        sy2 = lin[1](sx2)
+    sx2.copy_(x2)
+    g2.replay()
+    torch.cuda.synchronize()
     Q.SHARE_INPUT_QUANT = False
     ref2 = fwd(x2)
-    graph_ok = all(torch.equal(a, b) for a, b in zip(ref2, sy))
+    graph_ok = all(torch.equal(a, b) for a, b in zip(ref2, sy)) and torch.equal(ref2[1], sy2)
 with torch.enable_grad():
     Q.SHARE_INPUT_QUANT = True
     calls[0] = 0
